@@ -1,0 +1,888 @@
+// cntmc_api.cu -- the handle behind include/cntmc.h: host orchestration of the CUDA kernels in kernels.cuh.
+//
+// Reference citations (file:line) are into /root/reference/src.  There is no CPU execution path in this file: every
+// entry point that computes anything launches kernels, and fails with CNTMC_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/cntmc.h"
+#include "host_setup.h"
+#include "kernels.cuh"
+
+using namespace cntmc;
+
+namespace {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct StateError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct ReplayError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define CUDA_CHECK(expr)                                                                                   \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      throw CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                      std::to_string(__LINE__) + ")");                                                     \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T*     p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    release();
+    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    n = count;
+  }
+  void upload(const T* h, size_t count, cudaStream_t s) {
+    alloc(count);
+    if (count) CUDA_CHECK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s) { upload(v.data(), v.size(), s); }
+  void download(T* h, size_t count, cudaStream_t s) const {
+    if (count) CUDA_CHECK(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct cntmc_handle {
+  mutable std::string err;
+  json::Value         block;
+  Params              prm;
+  int                 device = -1;
+  cudaStream_t        stream = nullptr;
+
+  // host-side set-up state
+  Mesh      mesh;
+  bool      have_mesh = false;
+  HostTable table;
+  Sites     sites;
+  Domain    dom{};
+  Buckets   buckets;
+  Injection inj;
+  bool      initialised = false;
+  bool      contact_mode = false;
+  int       n_seg = 0;
+  std::vector<double>  area;
+  std::vector<int32_t> c1_sites, c2_sites;
+  int64_t              c1_pop = 0, c2_pop = 0;
+
+  std::vector<uint64_t> row_ptr;  // [N+1]
+  std::vector<double>   max_rate, inv_max_rate;
+  int64_t               midpoint_guards = 0;
+  double                csr_seconds = 0;
+
+  // device tables
+  DevBuf<FlyRec>  d_fly;
+  DevBuf<HopRec>  d_hop;
+  DevBuf<double>  d_cum;
+  DevBuf<int32_t> d_nbr, d_inject, d_c1, d_c2;
+  DevBuf<double>  d_theta, d_z, d_a1, d_a2, d_rates;
+  Tables          T{};
+
+  // excitons
+  int64_t          P = 0, capacity = 0;
+  DevBuf<double>   e_px, e_py, e_pz, e_dx, e_dy, e_dz, e_ff, e_ox, e_oy, e_oz;
+  DevBuf<int32_t>  e_site;
+  DevBuf<uint8_t>  e_heading;
+  DevBuf<uint32_t> e_ndraw, e_events, e_keys_out, e_iota, e_perm;
+  DevBuf<uint64_t> e_gid;
+  DevBuf<char>     sort_tmp;
+  bool             have_events = false;
+  DrawConfig       draws{};
+  bool             replay = false;
+  DevBuf<int64_t>  r_off;
+  DevBuf<int32_t>  r_draws;
+  DevBuf<double>   r_logs;
+
+  // reductions, diagnostics
+  DevBuf<double>             d_partial, d_sums;
+  DevBuf<int32_t>            d_flags;
+  DevBuf<unsigned long long> d_counters;
+  DevBuf<int32_t>            d_trace_sites, d_trace_counts;
+  int32_t                    trace_cap = 0;
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double      last_ms = 0;
+  int64_t     last_launches = 0;
+
+  // tuning
+  int64_t opt_chunk = 64;   // time steps per launch
+  int64_t opt_sort = 1;     // regroup excitons by activity between launches
+  int64_t opt_block = 128;  // threads per block of the hop kernel
+  int64_t opt_time_kernels = 0;  // CUDA events around every hop-kernel launch (bench.py's roofline figure)
+  std::vector<cudaEvent_t> kernel_events;
+  double  kernel_ms = 0;
+  int64_t kernel_launches = 0;
+
+  double  time = 0;  // monte_carlo::_time (never initialised by the reference, monte_carlo.h:45; starts at 0 here)
+  int64_t hops = 0, reinjections = 0, crossings = 0, probes = 0;
+
+  ~cntmc_handle() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+
+  ExcitonArrays arrays() {
+    ExcitonArrays S{};
+    S.px = e_px.p; S.py = e_py.p; S.pz = e_pz.p;
+    S.dx = e_dx.p; S.dy = e_dy.p; S.dz = e_dz.p;
+    S.ff = e_ff.p;
+    S.ox = contact_mode ? e_ox.p : nullptr;
+    S.oy = contact_mode ? e_oy.p : nullptr;
+    S.oz = contact_mode ? e_oz.p : nullptr;
+    S.site = e_site.p;
+    S.heading = e_heading.p;
+    S.ndraw = e_ndraw.p;
+    S.last_events = e_events.p;
+    S.gid = contact_mode ? e_gid.p : nullptr;
+    return S;
+  }
+  void alloc_excitons(int64_t cap) {
+    const size_t n = (size_t)cap;
+    e_px.alloc(n); e_py.alloc(n); e_pz.alloc(n);
+    e_dx.alloc(n); e_dy.alloc(n); e_dz.alloc(n);
+    e_ff.alloc(n);
+    e_site.alloc(n); e_heading.alloc(n); e_ndraw.alloc(n); e_events.alloc(n);
+    e_keys_out.alloc(n); e_iota.alloc(n); e_perm.alloc(n);
+    if (contact_mode) {
+      e_ox.alloc(n); e_oy.alloc(n); e_oz.alloc(n);
+      e_gid.alloc(n);
+    }
+    capacity = cap;
+  }
+};
+
+namespace {
+
+void use_device(const cntmc_t* h) {
+  if (h->device >= 0) CUDA_CHECK(cudaSetDevice(h->device));
+}
+
+void require(bool ok, const char* msg) {
+  if (!ok) throw std::invalid_argument(msg);
+}
+
+std::string expand_home(std::string path) {  // prepare_directory.hpp:12-16
+  if (!path.empty() && path[0] == '~') {
+    const char* home = std::getenv("HOME");
+    path = std::string(home ? home : "") + path.substr(1);
+  }
+  return path;
+}
+
+void check_flags(cntmc_t* h) {
+  int32_t flags[FLAG_COUNT];
+  h->d_flags.download(flags, FLAG_COUNT, h->stream);
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (flags[FLAG_REPLAY]) throw ReplayError("a replayed draw list ran out before the end of the run");
+  if (flags[FLAG_STUCK]) throw StateError("an exciton exceeded the chain-walk guard (coincident chain sites?)");
+}
+
+// ---- set-up common to kubo_init and init -------------------------------------------------------------------------------
+// monte_carlo.cpp:262-298 / monte_carlo.h:166-186: table, scatterers, trim, domain, buckets, set_max_rate
+void common_init(cntmc_t* h) {
+  require(h->have_mesh || !h->prm.mesh_dir.empty(), "no mesh: call cntmc_load_mesh / cntmc_set_mesh first");
+  if (!h->have_mesh) {
+    h->mesh = load_mesh(expand_home(h->prm.mesh_dir));
+    h->have_mesh = true;
+  }
+  if (h->table.empty()) h->table = make_rate_table(h->prm);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw CudaError("no CUDA device: this engine has no CPU execution path");
+  use_device(h);
+  h->sites = create_sites(h->mesh);
+  trim_sites(h->sites, h->prm.xlim, h->prm.ylim, h->prm.zlim);
+  h->dom = find_domain(h->sites);
+  const double  R = h->prm.max_hopping_radius;
+  const int64_t N = h->sites.N;
+  require(R > 0, "\"max hopping radius [m]\" must be positive");
+  h->buckets = build_buckets(h->sites, h->dom, R);
+
+  if (!h->ev0) {
+    CUDA_CHECK(cudaEventCreate(&h->ev0));
+    CUDA_CHECK(cudaEventCreate(&h->ev1));
+  }
+  cudaStream_t st = h->stream;
+  h->d_flags.alloc(FLAG_COUNT);
+  h->d_counters.alloc(CTR_COUNT);
+  CUDA_CHECK(cudaMemsetAsync(h->d_flags.p, 0, FLAG_COUNT * sizeof(int32_t), st));
+  CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, CTR_COUNT * sizeof(unsigned long long), st));
+
+  // rate table
+  const HostTable& t = h->table;
+  h->d_theta.upload(t.theta, st);
+  h->d_z.upload(t.z, st);
+  h->d_a1.upload(t.a1, st);
+  h->d_a2.upload(t.a2, st);
+  h->d_rates.upload(t.rates, st);
+
+  // site geometry in site order and in bucket order
+  std::vector<SiteGeom> geom((size_t)N), cell_geom((size_t)N);
+  std::vector<FlyRec>   fly((size_t)N);
+  for (int64_t i = 0; i < N; ++i) {
+    SiteGeom& g = geom[(size_t)i];
+    g.px = h->sites.pos[0][(size_t)i]; g.py = h->sites.pos[1][(size_t)i]; g.pz = h->sites.pos[2][(size_t)i];
+    g.ox = h->sites.orient[0][(size_t)i]; g.oy = h->sites.orient[1][(size_t)i]; g.oz = h->sites.orient[2][(size_t)i];
+    FlyRec& f = fly[(size_t)i];
+    f.x = g.px; f.y = g.py; f.z = g.pz;
+    f.left = h->sites.left[(size_t)i];
+    f.right = h->sites.right[(size_t)i];
+  }
+  for (int64_t q = 0; q < N; ++q) cell_geom[(size_t)q] = geom[(size_t)h->buckets.sites[(size_t)q]];
+  DevBuf<SiteGeom> d_geom, d_cell_geom;
+  DevBuf<int32_t>  d_cell_sites;
+  DevBuf<int64_t>  d_cell_start;
+  DevBuf<uint32_t> d_deg;
+  DevBuf<uint64_t> d_row_begin;
+  d_geom.upload(geom, st);
+  d_cell_geom.upload(cell_geom, st);
+  d_cell_sites.upload(h->buckets.sites, st);
+  d_cell_start.upload(h->buckets.start, st);
+  d_deg.alloc((size_t)N);
+  h->d_fly.upload(fly, st);
+  h->d_hop.alloc((size_t)N);
+
+  CsrArgs a{};
+  a.geom = d_geom.p;
+  a.cell_geom = d_cell_geom.p;
+  a.cell_sites = d_cell_sites.p;
+  a.cell_start = d_cell_start.p;
+  for (int c = 0; c < 3; ++c) {
+    a.nb[c] = h->buckets.n[c];
+    a.lo[c] = h->dom.lo[c];
+  }
+  a.radius = R;
+  a.N = N;
+  a.R.theta = h->d_theta.p; a.R.z = h->d_z.p; a.R.a1 = h->d_a1.p; a.R.a2 = h->d_a2.p; a.R.rates = h->d_rates.p;
+  a.R.n_theta = (int32_t)t.theta.size(); a.R.n_z = (int32_t)t.z.size();
+  a.R.n_a1 = (int32_t)t.a1.size(); a.R.n_a2 = (int32_t)t.a2.size();
+  a.deg = d_deg.p;
+  a.hop = h->d_hop.p;
+  a.flags = h->d_flags.p;
+  a.counters = h->d_counters.p;
+
+  const int      block = 128;
+  const unsigned grid = (unsigned)((N + block - 1) / block);
+  CUDA_CHECK(cudaEventRecord(h->ev0, st));
+  csr_rows_kernel<false><<<grid, block, 0, st>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  std::vector<uint32_t> deg((size_t)N);
+  d_deg.download(deg.data(), (size_t)N, st);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  h->row_ptr.assign((size_t)N + 1, 0);
+  for (int64_t i = 0; i < N; ++i) h->row_ptr[(size_t)i + 1] = h->row_ptr[(size_t)i] + deg[(size_t)i];
+  const uint64_t nnz = h->row_ptr[(size_t)N];
+  if (nnz >= (1ull << 32)) throw std::invalid_argument("neighbour table has >= 2^32 entries; not supported by this build");
+  d_row_begin.upload(h->row_ptr, st);
+  h->d_cum.alloc((size_t)nnz);
+  h->d_nbr.alloc((size_t)nnz);
+  a.row_begin = d_row_begin.p;
+  a.nbr = h->d_nbr.p;
+  a.cum = h->d_cum.p;
+  csr_rows_kernel<true><<<grid, block, 0, st>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaEventRecord(h->ev1, st));
+  int32_t            flags[FLAG_COUNT];
+  unsigned long long ctrs[CTR_COUNT];
+  h->d_flags.download(flags, FLAG_COUNT, st);
+  h->d_counters.download(ctrs, CTR_COUNT, st);
+  std::vector<HopRec> hop((size_t)N);
+  h->d_hop.download(hop.data(), (size_t)N, st);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->csr_seconds = ms * 1e-3;
+  h->midpoint_guards = (int64_t)ctrs[CTR_GUARD];
+  if (flags[FLAG_EMPTY_ROW])
+    throw StateError("a site has no neighbour inside the hopping radius (undefined behaviour in the reference, scatterer.h:91)");
+  h->max_rate.resize((size_t)N);
+  h->inv_max_rate.resize((size_t)N);
+  for (int64_t i = 0; i < N; ++i) {
+    h->max_rate[(size_t)i] = hop[(size_t)i].total;
+    h->inv_max_rate[(size_t)i] = hop[(size_t)i].inv_total;
+  }
+
+  h->T.fly = h->d_fly.p;
+  h->T.hop = h->d_hop.p;
+  h->T.cum = h->d_cum.p;
+  h->T.nbr = h->d_nbr.p;
+  h->T.velocity = h->prm.velocity;
+  h->time = 0;
+  h->hops = h->reinjections = 0;
+}
+
+template <typename Draws>
+void launch_create(cntmc_t* h, int64_t P, const int32_t* d_list, int32_t n_list) {
+  CreateArgs a{};
+  a.T = h->T;
+  a.S = h->arrays();
+  a.draws = h->draws;
+  a.P = P;
+  a.site_list = d_list;
+  a.n_list = n_list;
+  a.flags = h->d_flags.p;
+  const int block = 256;
+  create_excitons_kernel<Draws><<<(unsigned)((P + block - 1) / block), block, 0, h->stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void create_common(cntmc_t* h, int64_t P) {
+  require(h->initialised && !h->contact_mode, "call cntmc_kubo_init first");
+  require(P > 0, "number of particles must be positive");
+  require(!h->inj.sites.empty(), "the injection region holds no site");
+  use_device(h);
+  h->alloc_excitons(P);
+  h->P = P;
+  h->have_events = false;
+  h->time = 0;
+  h->hops = h->reinjections = 0;
+  h->crossings = h->probes = 0;
+  CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, CTR_COUNT * sizeof(unsigned long long), h->stream));
+  CUDA_CHECK(cudaMemsetAsync(h->e_events.p, 0, (size_t)P * sizeof(uint32_t), h->stream));
+  if (h->replay)
+    launch_create<ReplayDraws>(h, P, h->d_inject.p, (int32_t)h->inj.sites.size());
+  else
+    launch_create<PhiloxDraws>(h, P, h->d_inject.p, (int32_t)h->inj.sites.size());
+  check_flags(h);
+}
+
+// nsteps x kubo_step on the device; sums -> dev_sums[nsteps][4]
+void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
+  require(h->initialised && !h->contact_mode, "call cntmc_kubo_init first");
+  require(h->P > 0, "no excitons: call cntmc_kubo_create_particles first");
+  require(nsteps > 0, "nsteps must be positive");
+  use_device(h);
+  cudaStream_t  st = h->stream;
+  const int     block = (int)h->opt_block;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->opt_chunk, 256));
+  const unsigned grid = (unsigned)((h->P + block - 1) / block);
+  h->d_partial.alloc((size_t)grid * (size_t)std::min(chunk, nsteps) * 4);
+  h->last_launches = 0;
+  CUDA_CHECK(cudaEventRecord(h->ev0, st));
+  for (int64_t done = 0; done < nsteps; done += chunk) {
+    const int n = (int)std::min(chunk, nsteps - done);
+    const uint32_t* perm = nullptr;
+    if (h->opt_sort && h->have_events && h->trace_cap == 0) {
+      // heaviest excitons first, excitons of similar activity share a warp
+      iota_kernel<<<(unsigned)((h->P + 255) / 256), 256, 0, st>>>(h->e_iota.p, h->P);
+      size_t bytes = 0;
+      cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->e_events.p, h->e_keys_out.p, h->e_iota.p, h->e_perm.p,
+                                                (int)h->P, 0, 32, st);
+      h->sort_tmp.alloc(bytes);
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp.p, bytes, h->e_events.p, h->e_keys_out.p, h->e_iota.p,
+                                                           h->e_perm.p, (int)h->P, 0, 32, st));
+      perm = h->e_perm.p;
+      h->last_launches += 2;
+    }
+    KuboArgs a{};
+    a.T = h->T;
+    a.S = h->arrays();
+    a.draws = h->draws;
+    a.perm = perm;
+    a.P = h->P;
+    a.dt = dt;
+    a.nsteps = n;
+    a.partial = h->d_partial.p;
+    a.trace_sites = h->trace_cap ? h->d_trace_sites.p : nullptr;
+    a.trace_counts = h->trace_cap ? h->d_trace_counts.p : nullptr;
+    a.trace_cap = h->trace_cap;
+    a.flags = h->d_flags.p;
+    a.counters = h->d_counters.p;
+    const size_t smem = (size_t)(block / 32) * n * 4 * sizeof(double);
+    cudaEvent_t k0 = nullptr, k1 = nullptr;
+    if (h->opt_time_kernels) {
+      CUDA_CHECK(cudaEventCreate(&k0));
+      CUDA_CHECK(cudaEventCreate(&k1));
+      h->kernel_events.push_back(k0);
+      h->kernel_events.push_back(k1);
+      CUDA_CHECK(cudaEventRecord(k0, st));
+    }
+    if (h->replay)
+      kubo_flat_kernel<ReplayDraws><<<grid, block, smem, st>>>(a);
+    else
+      kubo_flat_kernel<PhiloxDraws><<<grid, block, smem, st>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    if (k1) CUDA_CHECK(cudaEventRecord(k1, st));
+    reduce_partials_kernel<<<n, 128, 0, st>>>(h->d_partial.p, (int)grid, n, dev_sums + done * 4);
+    CUDA_CHECK(cudaGetLastError());
+    h->last_launches += 2;
+    h->have_events = true;
+  }
+  CUDA_CHECK(cudaEventRecord(h->ev1, st));
+  for (int64_t s = 0; s < nsteps; ++s) h->time += dt;  // monte_carlo.cpp:341, one addition per step
+}
+
+void finish_step_host(cntmc_t* h, int64_t nsteps, double* msd_out) {
+  std::vector<double> sums((size_t)nsteps * 4);
+  h->d_sums.download(sums.data(), sums.size(), h->stream);
+  unsigned long long ctrs[CTR_COUNT];
+  h->d_counters.download(ctrs, CTR_COUNT, h->stream);
+  check_flags(h);  // synchronises
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_ms = ms;
+  h->kernel_ms = 0;
+  h->kernel_launches = (int64_t)h->kernel_events.size() / 2;
+  for (size_t k = 0; k + 1 < h->kernel_events.size(); k += 2) {
+    float kms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&kms, h->kernel_events[k], h->kernel_events[k + 1]));
+    h->kernel_ms += kms;
+    cudaEventDestroy(h->kernel_events[k]);
+    cudaEventDestroy(h->kernel_events[k + 1]);
+  }
+  h->kernel_events.clear();
+  h->reinjections = (int64_t)ctrs[CTR_REINJECT];
+  h->crossings = (int64_t)ctrs[CTR_CROSS];
+  h->probes = (int64_t)ctrs[CTR_PROBE];
+  for (int64_t s = 0; s < nsteps; ++s) {
+    h->hops += (int64_t)sums[(size_t)s * 4 + 3];
+    if (msd_out)
+      for (int c = 0; c < 3; ++c) msd_out[s * 3 + c] = sums[(size_t)s * 4 + c] / double(h->P);  // monte_carlo.cpp:402-404
+  }
+}
+
+template <typename F>
+int guarded(const cntmc_t* h, F&& body) {
+  try {
+    body();
+    return CNTMC_OK;
+  } catch (const CudaError& e) {
+    (h ? h->err : g_create_error) = e.what();
+    return CNTMC_ERR_CUDA;
+  } catch (const StateError& e) {
+    (h ? h->err : g_create_error) = e.what();
+    return CNTMC_ERR_STATE;
+  } catch (const ReplayError& e) {
+    (h ? h->err : g_create_error) = e.what();
+    return CNTMC_ERR_REPLAY;
+  } catch (const std::exception& e) {
+    (h ? h->err : g_create_error) = e.what();
+    return CNTMC_ERR_INVALID;
+  }
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+const char* cntmc_version(void) { return "cntmc-b200 0.1 (sm_100a)"; }
+
+const char* cntmc_last_error(const cntmc_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cntmc_create(const char* json_text, cntmc_t** out) {
+  if (out) *out = nullptr;
+  return guarded(nullptr, [&] {
+    require(json_text != nullptr && out != nullptr, "null argument");
+    std::unique_ptr<cntmc_t> h(new cntmc_t);
+    const json::Value      doc = json::parse(json_text);
+    h->block = mc_block(doc);
+    h->prm = parse_params(h->block);
+    *out = h.release();
+  });
+}
+
+void cntmc_destroy(cntmc_t* h) {
+  if (!h) return;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  delete h;
+}
+
+int cntmc_set_device(cntmc_t* h, int device) {
+  return guarded(h, [&] {
+    require(!h->initialised, "cntmc_set_device must precede initialisation");
+    h->device = device;
+  });
+}
+int cntmc_set_stream(cntmc_t* h, void* cuda_stream) {
+  return guarded(h, [&] { h->stream = (cudaStream_t)cuda_stream; });
+}
+
+int cntmc_load_mesh(cntmc_t* h, const char* dir) {
+  return guarded(h, [&] {
+    const std::string d = dir ? std::string(dir) : h->prm.mesh_dir;
+    require(!d.empty(), "no mesh directory given");
+    h->mesh = load_mesh(expand_home(d));
+    h->have_mesh = true;
+  });
+}
+
+int cntmc_set_mesh(cntmc_t* h, int64_t n_tubes, int64_t n_cols, const double* pos_nm, const double* orient) {
+  return guarded(h, [&] {
+    require(n_tubes > 0 && n_cols > 0 && pos_nm && orient, "bad mesh arguments");
+    const size_t N = (size_t)(n_tubes * n_cols);
+    h->mesh.n_tubes = n_tubes;
+    h->mesh.n_cols = n_cols;
+    for (int c = 0; c < 3; ++c) {
+      h->mesh.pos[c].assign(pos_nm + c * N, pos_nm + (c + 1) * N);
+      h->mesh.orient[c].assign(orient + c * N, orient + (c + 1) * N);
+    }
+    h->have_mesh = true;
+  });
+}
+
+int cntmc_set_rate_table(cntmc_t* h, const int32_t dims[4], const double* theta, const double* z, const double* a1,
+                         const double* a2, const double* rates) {
+  return guarded(h, [&] {
+    require(dims && theta && z && a1 && a2 && rates, "null argument");
+    require(dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && dims[3] > 0, "table dimensions must be positive");
+    require(!h->initialised, "cntmc_set_rate_table must precede initialisation");
+    h->table.theta.assign(theta, theta + dims[0]);
+    h->table.z.assign(z, z + dims[1]);
+    h->table.a1.assign(a1, a1 + dims[2]);
+    h->table.a2.assign(a2, a2 + dims[3]);
+    h->table.rates.assign(rates, rates + (size_t)dims[0] * dims[1] * dims[2] * dims[3]);
+  });
+}
+
+int cntmc_get_rate_table_dims(const cntmc_t* h, int32_t dims[4]) {
+  return guarded(h, [&] {
+    require(!h->table.empty(), "no rate table yet");
+    dims[0] = (int32_t)h->table.theta.size();
+    dims[1] = (int32_t)h->table.z.size();
+    dims[2] = (int32_t)h->table.a1.size();
+    dims[3] = (int32_t)h->table.a2.size();
+  });
+}
+int cntmc_get_rate_table(const cntmc_t* h, double* theta, double* z, double* a1, double* a2, double* rates) {
+  return guarded(h, [&] {
+    require(!h->table.empty(), "no rate table yet");
+    const HostTable& t = h->table;
+    if (theta) std::copy(t.theta.begin(), t.theta.end(), theta);
+    if (z) std::copy(t.z.begin(), t.z.end(), z);
+    if (a1) std::copy(t.a1.begin(), t.a1.end(), a1);
+    if (a2) std::copy(t.a2.begin(), t.a2.end(), a2);
+    if (rates) std::copy(t.rates.begin(), t.rates.end(), rates);
+  });
+}
+
+int cntmc_kubo_init(cntmc_t* h) {
+  return guarded(h, [&] {
+    h->contact_mode = false;
+    common_init(h);
+    h->inj = injection_region(h->sites, h->dom, h->prm.n_sections);
+    h->d_inject.upload(h->inj.sites, h->stream);
+    h->T.inject = h->d_inject.p;
+    h->T.n_inject = (int32_t)h->inj.sites.size();
+    for (int c = 0; c < 3; ++c) {
+      h->T.rem_lo[c] = h->inj.rem_lo[c];
+      h->T.rem_hi[c] = h->inj.rem_hi[c];
+    }
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->initialised = true;
+  });
+}
+
+int cntmc_kubo_create_particles(cntmc_t* h, int64_t n_particles, uint64_t seed, uint64_t first_global_id) {
+  return guarded(h, [&] {
+    h->replay = false;
+    h->draws = DrawConfig{};
+    h->draws.seed = seed;
+    h->draws.first_gid = first_global_id;
+    create_common(h, n_particles > 0 ? n_particles : h->prm.n_particles);
+  });
+}
+
+int cntmc_kubo_create_particles_replay(cntmc_t* h, int64_t P, const int64_t* offsets, const int32_t* draws_in,
+                                       const double* logs) {
+  return guarded(h, [&] {
+    require(P > 0 && offsets && draws_in, "bad replay arguments");
+    use_device(h);
+    const size_t total = (size_t)offsets[P];
+    h->r_off.upload(offsets, (size_t)P + 1, h->stream);
+    h->r_draws.upload(draws_in, total, h->stream);
+    if (logs) h->r_logs.upload(logs, total, h->stream);
+    h->replay = true;
+    h->draws = DrawConfig{};
+    h->draws.replay_off = h->r_off.p;
+    h->draws.replay_draws = h->r_draws.p;
+    h->draws.replay_logs = logs ? h->r_logs.p : nullptr;
+    create_common(h, P);
+  });
+}
+
+int cntmc_kubo_step(cntmc_t* h, double dt, int64_t nsteps, double* msd_out) {
+  return guarded(h, [&] {
+    require(nsteps > 0, "nsteps must be positive");
+    use_device(h);
+    h->d_sums.alloc((size_t)nsteps * 4);
+    kubo_step_device(h, dt, nsteps, h->d_sums.p);
+    finish_step_host(h, nsteps, msd_out);
+  });
+}
+
+int cntmc_kubo_step_dev(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
+  return guarded(h, [&] {
+    require(dev_sums != nullptr, "null device buffer");
+    kubo_step_device(h, dt, nsteps, dev_sums);
+  });
+}
+
+int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P, int32_t* site, double* pos, double* delta,
+                               double* ff, uint8_t* heading, uint32_t* ndraw, double* msd_out) {
+  return guarded(h, [&] {
+    require(h->initialised && !h->contact_mode, "call cntmc_kubo_init first");
+    require(P > 0 && site && pos && delta && ff && heading && ndraw, "bad host-state arguments");
+    use_device(h);
+    cudaStream_t st = h->stream;
+    if (P > h->capacity) h->alloc_excitons(P);
+    if (P != h->P) h->have_events = false;
+    h->P = P;
+    const size_t n = (size_t)P;
+    h->e_site.upload(site, n, st);
+    h->e_px.upload(pos, n, st); h->e_py.upload(pos + n, n, st); h->e_pz.upload(pos + 2 * n, n, st);
+    h->e_dx.upload(delta, n, st); h->e_dy.upload(delta + n, n, st); h->e_dz.upload(delta + 2 * n, n, st);
+    h->e_ff.upload(ff, n, st);
+    h->e_heading.upload(heading, n, st);
+    h->e_ndraw.upload(ndraw, n, st);
+    h->d_sums.alloc((size_t)nsteps * 4);
+    kubo_step_device(h, dt, nsteps, h->d_sums.p);
+    h->e_site.download(site, n, st);
+    h->e_px.download(pos, n, st); h->e_py.download(pos + n, n, st); h->e_pz.download(pos + 2 * n, n, st);
+    h->e_dx.download(delta, n, st); h->e_dy.download(delta + n, n, st); h->e_dz.download(delta + 2 * n, n, st);
+    h->e_ff.download(ff, n, st);
+    h->e_heading.download(heading, n, st);
+    h->e_ndraw.download(ndraw, n, st);
+    finish_step_host(h, nsteps, msd_out);
+  });
+}
+
+double  cntmc_time(const cntmc_t* h) { return h->time; }
+double  cntmc_kubo_max_time(const cntmc_t* h) { return h->prm.max_time; }
+double  cntmc_time_step(const cntmc_t* h) { return h->prm.time_step; }
+int64_t cntmc_number_of_particles(const cntmc_t* h) { return h->P; }
+int64_t cntmc_hops(const cntmc_t* h) { return h->hops; }
+int64_t cntmc_reinjections(const cntmc_t* h) { return h->reinjections; }
+int64_t cntmc_crossings(const cntmc_t* h) { return h->crossings; }
+int64_t cntmc_probes(const cntmc_t* h) { return h->probes; }
+
+// ---- contact flavour: see contacts.cuh (added once the Green-Kubo path is parity-green) ------------------------------
+int cntmc_init(cntmc_t* h, int64_t, int64_t, uint64_t, int64_t) {
+  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+}
+int cntmc_step(cntmc_t* h, double, int64_t, int64_t*, int64_t*) {
+  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+}
+int cntmc_step_dev(cntmc_t* h, double, int64_t, int64_t*) {
+  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+}
+int cntmc_get_area(const cntmc_t* h, double*) {
+  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+}
+int cntmc_num_contact_sites(const cntmc_t* h, int, int64_t*) {
+  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+}
+int cntmc_get_contact_sites(const cntmc_t* h, int, int32_t*) {
+  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+}
+int cntmc_number_of_segments(const cntmc_t* h) { return h->prm.n_seg; }
+
+// ---- read-back -----------------------------------------------------------------------------------------------------------
+int cntmc_num_sites(const cntmc_t* h, int64_t* n) {
+  return guarded(h, [&] {
+    require(h->initialised, "not initialised");
+    *n = h->sites.N;
+  });
+}
+
+int cntmc_get_sites(const cntmc_t* h, double* pos, double* orient, int32_t* left, int32_t* right, double* max_rate,
+                    double* inv_max_rate) {
+  return guarded(h, [&] {
+    require(h->initialised, "not initialised");
+    const size_t N = (size_t)h->sites.N;
+    for (int c = 0; c < 3; ++c) {
+      if (pos) std::copy(h->sites.pos[c].begin(), h->sites.pos[c].end(), pos + c * N);
+      if (orient) std::copy(h->sites.orient[c].begin(), h->sites.orient[c].end(), orient + c * N);
+    }
+    if (left) std::copy(h->sites.left.begin(), h->sites.left.end(), left);
+    if (right) std::copy(h->sites.right.begin(), h->sites.right.end(), right);
+    if (max_rate) std::copy(h->max_rate.begin(), h->max_rate.end(), max_rate);
+    if (inv_max_rate) std::copy(h->inv_max_rate.begin(), h->inv_max_rate.end(), inv_max_rate);
+  });
+}
+
+int cntmc_get_domain(const cntmc_t* h, double d[6]) {
+  return guarded(h, [&] {
+    require(h->initialised, "not initialised");
+    for (int c = 0; c < 3; ++c) {
+      d[c] = h->dom.lo[c];
+      d[3 + c] = h->dom.hi[c];
+    }
+  });
+}
+int cntmc_get_removal_domain(const cntmc_t* h, double d[6]) {
+  return guarded(h, [&] {
+    require(h->initialised && !h->contact_mode, "not initialised in Green-Kubo mode");
+    for (int c = 0; c < 3; ++c) {
+      d[c] = h->inj.rem_lo[c];
+      d[3 + c] = h->inj.rem_hi[c];
+    }
+  });
+}
+int cntmc_num_inject(const cntmc_t* h, int64_t* n) {
+  return guarded(h, [&] {
+    require(h->initialised && !h->contact_mode, "not initialised in Green-Kubo mode");
+    *n = (int64_t)h->inj.sites.size();
+  });
+}
+int cntmc_get_inject(const cntmc_t* h, int32_t* ids) {
+  return guarded(h, [&] {
+    require(h->initialised && !h->contact_mode, "not initialised in Green-Kubo mode");
+    std::copy(h->inj.sites.begin(), h->inj.sites.end(), ids);
+  });
+}
+
+int cntmc_csr_nnz(const cntmc_t* h, int64_t* nnz) {
+  return guarded(h, [&] {
+    require(h->initialised, "not initialised");
+    *nnz = (int64_t)h->row_ptr.back();
+  });
+}
+int cntmc_get_csr(const cntmc_t* h, int64_t* row_ptr, int32_t* nbr, double* cum) {
+  return guarded(h, [&] {
+    require(h->initialised, "not initialised");
+    use_device(h);
+    const size_t nnz = (size_t)h->row_ptr.back();
+    if (row_ptr)
+      for (size_t i = 0; i < h->row_ptr.size(); ++i) row_ptr[i] = (int64_t)h->row_ptr[i];
+    if (nbr) h->d_nbr.download(nbr, nnz, h->stream);
+    if (cum) h->d_cum.download(cum, nnz, h->stream);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  });
+}
+int64_t cntmc_csr_midpoint_guards(const cntmc_t* h) { return h->midpoint_guards; }
+double  cntmc_csr_build_seconds(const cntmc_t* h) { return h->csr_seconds; }
+
+int cntmc_get_particles(const cntmc_t* h, int32_t* site, double* pos, double* delta, double* ff, uint8_t* heading,
+                        uint32_t* ndraw) {
+  return guarded(h, [&] {
+    require(h->P > 0, "no excitons");
+    use_device(h);
+    const size_t n = (size_t)h->P;
+    cudaStream_t st = h->stream;
+    if (site) h->e_site.download(site, n, st);
+    if (pos) {
+      h->e_px.download(pos, n, st);
+      h->e_py.download(pos + n, n, st);
+      h->e_pz.download(pos + 2 * n, n, st);
+    }
+    if (delta) {
+      h->e_dx.download(delta, n, st);
+      h->e_dy.download(delta + n, n, st);
+      h->e_dz.download(delta + 2 * n, n, st);
+    }
+    if (ff) h->e_ff.download(ff, n, st);
+    if (heading) h->e_heading.download(heading, n, st);
+    if (ndraw) h->e_ndraw.download(ndraw, n, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int cntmc_get_old_pos(const cntmc_t* h, double* old_pos) {
+  return guarded(h, [&] {
+    require(h->contact_mode && h->P > 0, "old positions are kept in contact mode only");
+    use_device(h);
+    const size_t n = (size_t)h->P;
+    h->e_ox.download(old_pos, n, h->stream);
+    h->e_oy.download(old_pos + n, n, h->stream);
+    h->e_oz.download(old_pos + 2 * n, n, h->stream);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int cntmc_trace_enable(cntmc_t* h, int32_t cap) {
+  return guarded(h, [&] {
+    require(h->P > 0, "no excitons");
+    use_device(h);
+    h->trace_cap = cap;
+    if (cap > 0) {
+      h->d_trace_sites.alloc((size_t)h->P * cap);
+      h->d_trace_counts.alloc((size_t)h->P);
+      CUDA_CHECK(cudaMemsetAsync(h->d_trace_counts.p, 0, (size_t)h->P * sizeof(int32_t), h->stream));
+    }
+  });
+}
+int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites_out) {
+  return guarded(h, [&] {
+    require(h->trace_cap > 0, "tracing is off");
+    use_device(h);
+    if (counts) h->d_trace_counts.download(counts, (size_t)h->P, h->stream);
+    if (sites_out) h->d_trace_sites.download(sites_out, (size_t)h->P * h->trace_cap, h->stream);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
+  return guarded(h, [&] {
+    const std::string k = name ? name : "";
+    if (k == "chunk_steps") {
+      require(value >= 1 && value <= 256, "chunk_steps must be in [1, 256]");
+      h->opt_chunk = value;
+    } else if (k == "sort") {
+      h->opt_sort = value ? 1 : 0;
+    } else if (k == "block") {
+      require(value == 32 || value == 64 || value == 128, "block must be 32, 64 or 128");
+      h->opt_block = value;
+    } else if (k == "time_kernels") {
+      h->opt_time_kernels = value ? 1 : 0;
+    } else {
+      throw std::invalid_argument("unknown option \"" + k + "\"");
+    }
+  });
+}
+int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
+  const std::string k = name ? name : "";
+  if (k == "chunk_steps") return h->opt_chunk;
+  if (k == "sort") return h->opt_sort;
+  if (k == "block") return h->opt_block;
+  return -1;
+}
+double  cntmc_last_step_ms(const cntmc_t* h) { return h->last_ms; }
+int64_t cntmc_last_step_launches(const cntmc_t* h) { return h->last_launches; }
+int cntmc_sync(cntmc_t* h) {
+  return guarded(h, [&] {
+    require(h->initialised, "not initialised");
+    use_device(h);
+    unsigned long long ctrs[CTR_COUNT];
+    h->d_counters.download(ctrs, CTR_COUNT, h->stream);
+    check_flags(h);  // synchronises the stream, raises what the asynchronous calls could not report
+    h->reinjections = (int64_t)ctrs[CTR_REINJECT];
+    h->crossings = (int64_t)ctrs[CTR_CROSS];
+    h->probes = (int64_t)ctrs[CTR_PROBE];
+  });
+}
+double  cntmc_last_kernel_ms(const cntmc_t* h) { return h->kernel_ms; }
+int64_t cntmc_last_kernel_launches(const cntmc_t* h) { return h->kernel_launches; }
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// host_setup.h -- order-defining set-up of the simulation, done once on the host.
+//
+// These steps are cheap (O(N)) but they fix the enumeration order of every neighbour list and therefore the bits of
+// the cumulative rates, so they follow the reference exactly.  Reference citations are into /root/reference/src.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "json_min.h"
+
+namespace cntmc {
+
+// The "exciton monte carlo" block of input.json
+struct Params {
+  std::string           mesh_dir, output_dir;
+  bool                  keep_old_results = true;
+  std::string           rate_type;                         // davoody | forster | wong   (monte_carlo.cpp:27-59)
+  std::array<double, 3> zshift{}, ashift1{}, ashift2{}, theta_deg{};  // [start, stop, count]
+  double                max_hopping_radius = 0;            // monte_carlo.cpp:256
+  double                velocity = 0;                      // monte_carlo.cpp:259
+  int                   n_seg = 0;                         // monte_carlo.h:164 (contact mode)
+  std::array<double, 2> xlim{}, ylim{}, zlim{};            // monte_carlo.cpp:276-278
+  double                time_step = 0;                     // main.cpp:62
+  int                   n_sections = 0;                    // monte_carlo.cpp:300
+  double                max_time = 0;                      // monte_carlo.cpp:304
+  int64_t               n_particles = 0;                   // monte_carlo.cpp:309
+  bool                  has_table_grids = false;
+};
+
+// `doc` is either a whole input.json (with an "exciton monte carlo" member, main.cpp:46-49) or that block itself.
+const json::Value& mc_block(const json::Value& doc);
+Params             parse_params(const json::Value& block);
+
+std::vector<double> linspace(double start, double end, int64_t n);
+
+struct HostTable {
+  std::vector<double> theta, z, a1, a2, rates;  // rates in [theta][z][a1][a2] C order
+  bool                empty() const { return rates.empty(); }
+};
+// monte_carlo::create_scattering_table for "forster" (gamma0 = 1e15) and "wong" (1e13)  (monte_carlo.cpp:24-61, 156-200)
+HostTable make_rate_table(const Params& p);
+
+struct Mesh {
+  int64_t             n_tubes = 0, n_cols = 0;
+  std::vector<double> pos[3], orient[3];  // tube-major, positions in nm
+};
+// the six single_cnt.{pos,orient}.{x,y,z}.dat files (monte_carlo.h:206-245); Armadillo arma_ascii or raw ASCII
+Mesh load_mesh(const std::string& dir);
+
+struct Sites {
+  int64_t              N = 0;
+  std::vector<double>  pos[3], orient[3];  // metres
+  std::vector<int32_t> left, right;
+};
+Sites create_sites(const Mesh& m);  // monte_carlo.h:247-263
+// monte_carlo::trim_scats (monte_carlo.h:722-782): same surviving order and links as the reference's swap loop
+void trim_sites(Sites& s, const std::array<double, 2>& xlim, const std::array<double, 2>& ylim,
+                const std::array<double, 2>& zlim);
+
+struct Domain {
+  double lo[3], hi[3];
+};
+Domain find_domain(const Sites& s);  // monte_carlo.h:328-340
+
+struct Buckets {
+  int                  n[3] = {0, 0, 0};
+  std::vector<int64_t> start;  // [ncell+1]
+  std::vector<int32_t> sites;  // [N], ascending site index inside each cell
+};
+Buckets build_buckets(const Sites& s, const Domain& d, double radius);  // monte_carlo.h:375-395
+
+struct Injection {
+  std::vector<int32_t> sites;  // monte_carlo.cpp:203-228
+  double               rem_lo[3], rem_hi[3];  // monte_carlo.cpp:231-251
+};
+Injection injection_region(const Sites& s, const Domain& d, int n_sections);
+
+// contact mode
+std::vector<double>  slab_areas(const Sites& s, const Domain& d, int n_seg);              // monte_carlo.h:646-688
+std::vector<int32_t> contact_sites(const Sites& s, const Domain& d, int n_seg, int i);  // monte_carlo.h:494-516
+std::vector<int32_t> slab_sites_half_open(const Sites& s, const Domain& d, int n_seg, int i);  // monte_carlo.h:296-301
+
+}  // namespace cntmc

@@ -1,0 +1,163 @@
+/* cntmc.h -- C ABI of libcntmc.so, the B200-native exciton hop engine.
+ *
+ * The reference (amirhosseindavoody/cnt_film_monte_carlo) has no plugin or FFI boundary: main() calls C++ methods
+ * on one mc::monte_carlo object (src/main.cpp:64-76, 85-105).  This header is the boundary a maintainer binds
+ * instead: one opaque handle per simulation, one entry point per mc::monte_carlo method on the hot path.  Each entry
+ * point names the reference interface it replaces (file:line into /root/reference/src).  INTEGRATION.md shows the
+ * C++ shim (class mc::monte_carlo re-implemented over these calls) and the ctypes binding.
+ *
+ * Conventions: every function returning int gives 0 on success and a negative code on failure; the message is
+ * available from cntmc_last_error(h) (or cntmc_last_error(NULL) when no handle exists yet).  No exception crosses the
+ * boundary.  The caller owns every host buffer it passes; the handle owns all device memory.  One host thread per
+ * handle; one handle drives one GPU.  All pointers are plain host pointers unless the name says "dev".
+ * There is no CPU execution path: without a CUDA device cntmc_kubo_init() fails with CNTMC_ERR_CUDA.
+ */
+#ifndef CNTMC_H
+#define CNTMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cntmc_handle cntmc_t;
+
+enum {
+  CNTMC_OK = 0,
+  CNTMC_ERR_INVALID = -1, /* bad argument / bad JSON / call out of order (std::invalid_argument in the reference) */
+  CNTMC_ERR_CUDA = -2,    /* a CUDA runtime call failed, or no device */
+  CNTMC_ERR_STATE = -3,   /* simulation reached a state the reference leaves undefined (e.g. a site with no neighbour,
+                             scatterer.h:91) or a bounded device loop hit its guard */
+  CNTMC_ERR_REPLAY = -4   /* a replayed draw list ran out */
+};
+
+/* ---- life cycle ------------------------------------------------------------------------------------------------- */
+
+/* monte_carlo::monte_carlo(const nlohmann::json&)  monte_carlo/monte_carlo.h:116-136  (+ main.cpp:41-54).
+ * json_text is either a whole input.json or its "exciton monte carlo" block.  Directory preparation (output
+ * rotation, prepare_directory.hpp) is left to the host shim; the handle itself touches no files except the mesh. */
+int  cntmc_create(const char* json_text, cntmc_t** out);
+void cntmc_destroy(cntmc_t* h);
+const char* cntmc_last_error(const cntmc_t* h);
+const char* cntmc_version(void);
+
+/* CUDA placement (call before *_init).  device < 0 keeps the current device; stream is a cudaStream_t (NULL = the
+ * legacy default stream).  All kernels and copies of the handle are issued on that stream. */
+int cntmc_set_device(cntmc_t* h, int device);
+int cntmc_set_stream(cntmc_t* h, void* cuda_stream);
+
+/* ---- inputs ----------------------------------------------------------------------------------------------------- */
+
+/* monte_carlo::create_scatterers  monte_carlo.h:199-271: reads the six single_cnt.{pos,orient}.{x,y,z}.dat files.
+ * dir == NULL uses "mesh input directory" of the JSON ('~' expanded like prepare_directory.hpp:12-16). */
+int cntmc_load_mesh(cntmc_t* h, const char* dir);
+/* same, from memory: pos_nm and orient are [3][n_tubes*n_cols] (x plane, y plane, z plane; tube-major), positions in nm */
+int cntmc_set_mesh(cntmc_t* h, int64_t n_tubes, int64_t n_cols, const double* pos_nm, const double* orient);
+
+/* scattering_struct  monte_carlo/scattering_struct.h:11-35: install a precomputed 4-D table (e.g. a "davoody" table
+ * saved by scattering_struct::save, :56-94) instead of building the closed-form one.  rates is [theta][z][a1][a2]. */
+int cntmc_set_rate_table(cntmc_t* h, const int32_t dims[4], const double* theta, const double* z_shift,
+                         const double* axis_shift_1, const double* axis_shift_2, const double* rates);
+int cntmc_get_rate_table_dims(const cntmc_t* h, int32_t dims[4]);
+int cntmc_get_rate_table(const cntmc_t* h, double* theta, double* z_shift, double* axis_shift_1, double* axis_shift_2,
+                         double* rates);
+
+/* ---- Green-Kubo flavour ------------------------------------------------------------------------------------------- */
+
+/* monte_carlo::kubo_init  monte_carlo/monte_carlo.cpp:254-305: rate table (create_scattering_table :24-61 for
+ * forster/wong), trim_scats, find_simulation_domain, create_scatterer_buckets, set_max_rate (here: the CSR
+ * neighbour-table build on the GPU), injection_region, get_removal_domain. */
+int cntmc_kubo_init(cntmc_t* h);
+
+/* monte_carlo::kubo_create_particles  monte_carlo.cpp:308-316.  n_particles <= 0 uses "number of particles for kubo
+ * simulation".  Exciton i gets the counter-based stream (seed, first_global_id + i): results do not depend on how a
+ * population is split over GPUs. */
+int cntmc_kubo_create_particles(cntmc_t* h, int64_t n_particles, uint64_t seed, uint64_t first_global_id);
+/* same, but every draw comes from a recorded list (the reference's own rand() stream, split per exciton):
+ * exciton i consumes draws[offsets[i] .. offsets[i+1]).  logs (may be NULL) holds log(draw/RAND_MAX) as computed by
+ * the host libm for each draw, which makes free-flight times bit-identical to a glibc run. */
+int cntmc_kubo_create_particles_replay(cntmc_t* h, int64_t n_particles, const int64_t* offsets, const int32_t* draws,
+                                       const double* logs);
+
+/* nsteps x { monte_carlo::kubo_step(dt)  monte_carlo.cpp:319-342 ; the ensemble averages written by
+ * kubo_save_avg_dispalcement_squared  :396-406 }.  msd_out (may be NULL) receives [nsteps][3] = <dx^2>,<dy^2>,<dz^2>
+ * after each step, averaged over this handle's excitons. */
+int cntmc_kubo_step(cntmc_t* h, double dt, int64_t nsteps, double* msd_out);
+/* same, but leaves the un-normalised sums on the device for a collective: dev_sums is a device pointer to
+ * [nsteps][4] doubles = sum dx^2, sum dy^2, sum dz^2, hops in that step.  Asynchronous on the handle's stream. */
+int cntmc_kubo_step_dev(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums);
+/* same as cntmc_kubo_step for a population that lives in HOST memory (like the reference's std::vector<particle>):
+ * uploads the state, steps, downloads it again.  Arrays as in cntmc_get_particles. */
+int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t n_particles, int32_t* site, double* pos,
+                               double* delta, double* ff, uint8_t* heading, uint32_t* ndraw, double* msd_out);
+
+double  cntmc_time(const cntmc_t* h);              /* monte_carlo::time            monte_carlo.h:139 */
+double  cntmc_kubo_max_time(const cntmc_t* h);     /* monte_carlo::kubo_max_time   monte_carlo.h:833 */
+double  cntmc_time_step(const cntmc_t* h);         /* "monte carlo time step"      main.cpp:62 */
+int64_t cntmc_number_of_particles(const cntmc_t* h); /* monte_carlo::number_of_particles monte_carlo.h:154 */
+int64_t cntmc_hops(const cntmc_t* h);              /* scattering events so far (the metric's unit) */
+int64_t cntmc_reinjections(const cntmc_t* h);
+/* bookkeeping behind the roofline's algorithmic bytes: chain sites crossed in flight and cumulative-rate entries probed */
+int64_t cntmc_crossings(const cntmc_t* h);
+int64_t cntmc_probes(const cntmc_t* h);
+
+/* ---- contact flavour ------------------------------------------------------------------------------------------------ */
+
+/* monte_carlo::init  monte_carlo.h:157-195 (contacts = first and last of "number of segments" slabs along y;
+ * create_particles :274-316 with a linear profile from c1_pop to c2_pop; the reference hard-codes 1100 and 0). */
+int cntmc_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_t capacity);
+/* nsteps x { monte_carlo::step(dt) :343-355 ; save_population_profile :566-573 ; save_currents :593-636 ;
+ * repopulate_contacts :443-455 }.  pop_out [nsteps][n_seg] excitons per slab, curr_out [nsteps][n_seg-1] net
+ * crossings per interface (raw counts; the shim divides by area*dy and area*dt like the reference's writers). */
+int cntmc_step(cntmc_t* h, double dt, int64_t nsteps, int64_t* pop_out, int64_t* curr_out);
+int cntmc_step_dev(cntmc_t* h, double dt, int64_t nsteps, int64_t* dev_bins /* [nsteps][2*n_seg-1] */);
+int cntmc_get_area(const cntmc_t* h, double* area /* [n_seg] */);                /* monte_carlo::get_area :646-688 */
+int cntmc_num_contact_sites(const cntmc_t* h, int which, int64_t* n);           /* monte_carlo::contact_scats :494-516 */
+int cntmc_get_contact_sites(const cntmc_t* h, int which, int32_t* ids);
+int cntmc_number_of_segments(const cntmc_t* h);
+
+/* ---- read-back (parity tests, checkpoints, output writers) ------------------------------------------------------------ */
+
+int cntmc_num_sites(const cntmc_t* h, int64_t* n);
+/* post-trim site list: pos/orient [3][N] in metres, chain links, Gamma_i (scatterer::_max_rate) and its inverse */
+int cntmc_get_sites(const cntmc_t* h, double* pos, double* orient, int32_t* left, int32_t* right, double* max_rate,
+                    double* inv_max_rate);
+int cntmc_get_domain(const cntmc_t* h, double lo_hi[6]);          /* find_simulation_domain monte_carlo.h:328-340 */
+int cntmc_get_removal_domain(const cntmc_t* h, double lo_hi[6]);  /* get_removal_domain monte_carlo.cpp:231-251 */
+int cntmc_num_inject(const cntmc_t* h, int64_t* n);               /* injection_region monte_carlo.cpp:203-228 */
+int cntmc_get_inject(const cntmc_t* h, int32_t* ids);
+/* the neighbour table = scatterer::find_neighbors (scatterer.cpp:34-83) of every site, as CSR */
+int cntmc_csr_nnz(const cntmc_t* h, int64_t* nnz);
+int cntmc_get_csr(const cntmc_t* h, int64_t* row_ptr /* [N+1] */, int32_t* nbr /* [nnz] */, double* cum /* [nnz] */);
+/* pairs whose theta fell within 1e-9 grid pitches of a grid midpoint (device acos vs glibc acos could disagree) */
+int64_t cntmc_csr_midpoint_guards(const cntmc_t* h);
+double  cntmc_csr_build_seconds(const cntmc_t* h);
+
+/* exciton state: site [P], pos [3][P], delta [3][P] (particle::_delta_pos), ff [P], heading [P], ndraw [P]; any
+ * pointer may be NULL */
+int cntmc_get_particles(const cntmc_t* h, int32_t* site, double* pos, double* delta, double* ff, uint8_t* heading,
+                        uint32_t* ndraw);
+int cntmc_get_old_pos(const cntmc_t* h, double* old_pos /* [3][P] */);
+
+/* record the site reached by each scattering event of the next cntmc_kubo_step call (tests only; cap events per
+ * exciton).  After the step: counts [P] and sites [P][cap]. */
+int cntmc_trace_enable(cntmc_t* h, int32_t cap);
+int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites);
+
+/* ---- tuning (never changes results) ------------------------------------------------------------------------------------ */
+int cntmc_set_option(cntmc_t* h, const char* name, int64_t value);
+int64_t cntmc_get_option(const cntmc_t* h, const char* name);
+/* device time of the last kubo_step / step call's kernels in milliseconds (CUDA events on the handle's stream) */
+double cntmc_last_step_ms(const cntmc_t* h);
+int64_t cntmc_last_step_launches(const cntmc_t* h);
+/* wait for the handle's stream, report errors of asynchronous (*_dev) calls, refresh the cumulative counters */
+int cntmc_sync(cntmc_t* h);
+/* with option "time_kernels" = 1: summed device time and count of the hop-kernel launches of the last step call */
+double  cntmc_last_kernel_ms(const cntmc_t* h);
+int64_t cntmc_last_kernel_launches(const cntmc_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNTMC_H */

@@ -943,3 +943,9 @@ void t1_contact_iteration(t1_sim* s, double dt, int64_t* pop, int64_t* curr) {
   repopulate(s, ymin, ymin + dy, s->c1_pop, s->c1, s->n_c1);
   repopulate(s, ymin + (double)(n - 1) * dy, ymax, s->c2_pop, s->c2, s->n_c2);
 }
+
+/* log(r / RAND_MAX) with the host libm, for every recorded draw: fed to the engine's replay mode so that free-flight
+ * times are bit-identical to a glibc run (scatterer.h:79). */
+void t1_log_ratios(const int32_t* draws, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = log((double)draws[i] / (double)T1_RAND_MAX);
+}

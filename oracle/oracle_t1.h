@@ -25,6 +25,7 @@ int32_t t1_philox_draw(uint64_t seed, uint64_t exciton, uint64_t k); /* 31-bit d
 void   t1_forster_table(double gamma0, const int32_t dims[4], const double* theta, const double* z, const double* a1,
                         const double* a2, double* rates);
 int64_t t1_select(const double* cum, int64_t d, double dice); /* scatterer.cpp:18-30 */
+void   t1_log_ratios(const int32_t* draws, int64_t n, double* out); /* host libm log(r/RAND_MAX) */
 
 /* ---- simulation object ------------------------------------------------------------------------------------- */
 t1_sim* t1_create(void);

@@ -42,6 +42,8 @@ class T0:
         L.t0_open_contacts.argtypes = [C.c_char_p, C.c_uint]
         L.t0_kubo_step_verbatim.argtypes = [C.c_double, C.c_int64, C.c_void_p, C.c_int]
         L.t0_kubo_step_logged.argtypes = [C.c_double, C.c_int64, C.c_void_p]
+        L.t0_kubo_step_omp.argtypes = [C.c_double, C.c_int64]
+        L.t0_kubo_step_omp.restype = C.c_int64
         L.t0_kubo_create_particles_logged.argtypes = [C.c_int64]
         L.t0_draw_counts.argtypes = [C.c_void_p, C.c_int64]
         L.t0_draws.argtypes = [C.c_void_p, C.c_int64]
@@ -151,6 +153,10 @@ class T0:
         msd = np.empty((nsteps, 3))
         self.L.t0_kubo_step_logged(dt, nsteps, _p(msd))
         return msd
+
+    def kubo_step_omp(self, dt: float, nsteps: int) -> int:
+        """The reference's OpenMP particle loop; returns the number of re-injections (for exact hop counting)."""
+        return self.L.t0_kubo_step_omp(dt, nsteps)
 
     def draws(self, P: int):
         """Per-exciton draw log in CSR form: ``(offsets[P+1], flat int32 draws)``."""

@@ -52,6 +52,7 @@ bool                              g_log_on = false;
 int64_t                           g_cur = -1;  // exciton currently consuming draws (-1: unattributed)
 std::vector<std::vector<int32_t>> g_draws;     // per exciton, in consumption order
 int64_t                           g_total_draws = 0;
+int                               g_threads = 1;  // OpenMP team size for the reference's parallel regions
 
 struct cout_silencer {
   std::streambuf* old;
@@ -72,7 +73,7 @@ void attribute_to(int64_t i) {
 // glibc: int rand(void) { return (int) __random(); }   -- same stream, now observable.
 extern "C" int rand(void) {
   const int r = (int)random();
-  ++g_total_draws;
+  __atomic_fetch_add(&g_total_draws, 1, __ATOMIC_RELAXED);
   if (g_log_on && g_cur >= 0) g_draws[g_cur].push_back(r);
   return r;
 }
@@ -88,7 +89,7 @@ int64_t t0_total_draws() { return g_total_draws; }
 int t0_open(const char* json_path, unsigned seed) {
   try {
     cout_silencer quiet;
-    omp_set_num_threads(1);
+    omp_set_num_threads(g_threads);
     srandom(seed);
     std::ifstream  f(json_path);
     nlohmann::json j;
@@ -110,7 +111,7 @@ int t0_open(const char* json_path, unsigned seed) {
 int t0_open_contacts(const char* json_path, unsigned seed) {
   try {
     cout_silencer quiet;
-    omp_set_num_threads(1);
+    omp_set_num_threads(g_threads);
     srandom(seed);
     std::ifstream  f(json_path);
     nlohmann::json j;
@@ -130,7 +131,10 @@ int t0_open_contacts(const char* json_path, unsigned seed) {
 
 void t0_close() { g_sim.reset(); }
 
-void t0_set_threads(int n) { omp_set_num_threads(n); }
+void t0_set_threads(int n) {
+  g_threads = n > 0 ? n : 1;
+  omp_set_num_threads(g_threads);
+}
 
 // ---- read-only views of the set-up state ------------------------------------------------------------------------
 int64_t t0_num_sites() { return (int64_t)g_sim->_all_scat_list.size(); }
@@ -312,6 +316,32 @@ void t0_kubo_step_logged(double dt, int64_t nsteps, double* msd /*[nsteps][3]*/)
     if (msd) msd_row(msd + 3 * s);
   }
   g_cur = -1;
+}
+
+// CPU-baseline timing loop: monte_carlo::kubo_step (monte_carlo.cpp:319-342) with its OpenMP parallel-for, plus a count
+// of re-injections so that hops = (draws - reinjections) / 2 is exact.  Draw logging must be off (not thread-safe).
+int64_t t0_kubo_step_omp(double dt, int64_t nsteps) {
+  auto&   sim = *g_sim;
+  int64_t reinj = 0;
+  g_cur = -1;
+  for (int64_t s = 0; s < nsteps; ++s) {
+#pragma omp parallel for reduction(+ : reinj)
+    for (unsigned i = 0; i < sim._particle_list.size(); ++i) {
+      mc::particle& p = sim._particle_list[i];
+      p.step(dt, sim._all_scat_list, sim._max_hopping_radius);
+      p.update_delta_pos();
+      if (arma::any(p.pos() < sim._removal_domain.first) || arma::any(sim._removal_domain.second < p.pos())) {
+        int                  dice = std::rand() % sim._inject_scats.size();
+        const mc::scatterer* sc = sim._inject_scats[dice];
+        arma::vec            pos = sc->pos();
+        p.set_pos(pos);
+        p.set_scatterer(sc);
+        ++reinj;
+      }
+    }
+    sim._time += dt;
+  }
+  return reinj;
 }
 
 int64_t t0_draw_count(int64_t i) { return (size_t)i < g_draws.size() ? (int64_t)g_draws[i].size() : 0; }

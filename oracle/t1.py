@@ -40,6 +40,7 @@ def _lib():
         "t1_philox_draw": (I32, [U64, U64, U64]),
         "t1_forster_table": (None, [D, V, V, V, V, V, V]),
         "t1_select": (I64, [V, I64, D]),
+        "t1_log_ratios": (None, [V, I64, V]),
         "t1_create": (V, []),
         "t1_destroy": (None, [V]),
         "t1_set_table": (None, [V, V, V, V, V, V, V]),
@@ -122,6 +123,14 @@ def philox_draw(seed: int, exciton: int, k: int) -> int:
 def select(cum: np.ndarray, dice: float) -> int:
     cum = np.ascontiguousarray(cum, np.float64)
     return lib().t1_select(_p(cum), len(cum), dice)
+
+
+def log_ratios(draws: np.ndarray) -> np.ndarray:
+    """log(r/RAND_MAX) for each draw, computed by the host libm (what the reference's ff_time evaluates)."""
+    d = np.ascontiguousarray(draws, np.int32)
+    out = np.empty(len(d))
+    lib().t1_log_ratios(_p(d), len(d), _p(out))
+    return out
 
 
 REF_PI = 3.141592  # helper/constants.h:10 (truncated on purpose: it defines the theta grid)

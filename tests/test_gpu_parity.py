@@ -1,0 +1,190 @@
+"""Parity of the CUDA engine (through the C ABI) with the golden vectors and the oracle.  Run with -m gpu on a B200."""
+import numpy as np
+import pytest
+
+from cnt_film_monte_carlo_b200 import film
+from cnt_film_monte_carlo_b200.engine import CntmcError, Engine
+from oracle import t1 as T1m
+from conftest import base_mc
+
+pytestmark = pytest.mark.gpu
+STATE_KEYS = ("site", "pos", "delta", "ff", "heading")
+
+
+def engine_for(g):
+    e = Engine(g.mc)
+    e.set_mesh(g.pos_nm, g.orient)
+    e.kubo_init()
+    return e
+
+
+def test_setup_and_neighbour_table_bit_exact(golden):
+    e = engine_for(golden)
+    sites = e.sites()
+    for k, v in golden.group("site_").items():
+        assert np.array_equal(sites[k], v), k
+    assert np.array_equal(e.domain(), golden.z["domain"]) and np.array_equal(e.removal_domain(), golden.z["removal"])
+    assert np.array_equal(e.inject(), golden.z["inject"])
+    tab = e.rate_table()
+    for k, v in golden.group("table_").items():
+        assert np.array_equal(tab[k], v), k
+    rp, nbr, cum = e.csr()
+    assert np.array_equal(rp, golden.z["row_ptr"])
+    assert np.array_equal(nbr, golden.z["nbr"])       # neighbour lists: same members, same order
+    assert np.array_equal(cum, golden.z["cum"])       # cumulative rates: bit for bit (<= 1e-12 rel required)
+    assert e.csr_midpoint_guards() == 0
+
+
+def test_replay_of_reference_draws_is_bit_exact(golden):
+    e = engine_for(golden)
+    e.kubo_create_particles_replay(golden.z["draw_off"], golden.z["draws"], golden.z["draw_logs"])
+    p0 = e.particles()
+    for k in ("site", "pos", "ff", "heading"):
+        assert np.array_equal(p0[k], golden.z["p0_" + k]), k
+    msd = e.kubo_step(golden.dt, golden.nsteps)
+    p1 = e.particles()
+    for k in STATE_KEYS:
+        assert np.array_equal(p1[k], golden.z["p1_" + k]), k
+    assert np.array_equal(p1["ndraw"], np.diff(golden.z["draw_off"]))
+    assert np.allclose(msd, golden.z["msd"], rtol=1e-12, atol=0)
+    assert e.time() == float(golden.z["time"])
+
+
+def test_replay_with_device_log_keeps_site_sequences(golden):
+    """Without the host's log values the free-flight times may differ in the last place; sites must not."""
+    e = engine_for(golden)
+    e.kubo_create_particles_replay(golden.z["draw_off"], golden.z["draws"], None)
+    e.kubo_step(golden.dt, golden.nsteps, want_msd=False)
+    p1 = e.particles()
+    assert np.array_equal(p1["site"], golden.z["p1_site"]) and np.array_equal(p1["heading"], golden.z["p1_heading"])
+    assert np.allclose(p1["pos"], golden.z["p1_pos"], rtol=1e-9, atol=1e-18)
+    assert np.allclose(p1["ff"], golden.z["p1_ff"], rtol=1e-9, atol=1e-24)
+
+
+def test_replay_list_too_short_is_reported(golden_small):
+    g = golden_small
+    e = engine_for(g)
+    off = g.z["draw_off"].copy()
+    cut = off.copy()
+    cut[1:] = np.minimum(off[1:], off[:-1] + 4)  # at most 4 draws per exciton
+    draws = np.concatenate([g.z["draws"][off[i]:cut[i + 1]] for i in range(g.P)])
+    noff = np.zeros_like(off)
+    np.cumsum(cut[1:] - off[:-1], out=noff[1:])
+    e.kubo_create_particles_replay(noff, draws, None)
+    with pytest.raises(CntmcError) as ei:
+        e.kubo_step(g.dt, g.nsteps)
+    assert ei.value.code == -4
+
+
+def test_philox_matches_oracle_site_sequences_and_state(golden):
+    P, nsteps = 96, 120
+    e = engine_for(golden)
+    e.kubo_create_particles(P, seed=777, first_global_id=5000)
+    e.trace_enable(1 << 13)
+    msd = e.kubo_step(golden.dt, nsteps)
+    t = T1m.T1()
+    t.kubo_init(golden.mc, golden.pos_nm, golden.orient)
+    t.draws_philox(777)
+    t.trace_sites(True)
+    t.create_particles(P, first_global_id=5000)
+    msd_t = t.kubo_step(golden.dt, nsteps)
+    pe, pt = e.particles(), t.particles()
+    assert np.array_equal(pe["site"], pt["site"]) and np.array_equal(pe["heading"], pt["heading"].astype(np.uint8))
+    # device log() vs glibc log() may differ in the last place of a free-flight time
+    assert np.allclose(pe["pos"], pt["pos"], rtol=1e-9, atol=1e-18) and np.allclose(pe["ff"], pt["ff"], rtol=1e-9, atol=1e-24)
+    counts, sites = e.trace()
+    off_t, flat_t = t.traced_sites(5000 + P)
+    assert np.array_equal(counts, np.diff(off_t)[5000:])
+    flat_e = np.concatenate([sites[i, :counts[i]] for i in range(P)])
+    assert np.array_equal(flat_e, flat_t)          # every scattering event lands on the same site, in the same order
+    assert e.hops() == t.hops() and e.reinjections() == t.reinjections()
+    assert np.allclose(msd, msd_t, rtol=1e-9, atol=0)
+
+
+def test_chunking_sorting_and_block_size_do_not_change_results():
+    pos, ori = film.film(NT=150, NP=60, a=5.0, LX=300.0, LY=80.0, seed=5)
+    mc = base_mc()
+    states, msds = [], []
+    for opts in (dict(chunk_steps=64, sort=1, block=128), dict(chunk_steps=7, sort=0, block=64), dict(chunk_steps=1, sort=1, block=32),
+                 dict(chunk_steps=200, sort=1, block=128)):
+        e = Engine(mc)
+        e.set_mesh(pos, ori)
+        for k, v in opts.items():
+            e.set_option(k, v)
+        e.kubo_init()
+        e.kubo_create_particles(5000, seed=4)
+        m = [e.kubo_step(1e-13, 50), e.kubo_step(1e-13, 37)]
+        states.append(e.particles())
+        msds.append(np.concatenate(m))
+        hops = e.hops()
+    for s in states[1:]:
+        assert all(np.array_equal(s[k], states[0][k]) for k in s)  # per-exciton results: bit-identical
+    for m in msds[1:]:
+        assert np.allclose(m, msds[0], rtol=1e-13, atol=0)          # ensemble sums: only the summation order moves
+    assert hops > 5000
+
+
+def test_host_state_call_equals_resident_call(golden_small):
+    g = golden_small
+    a, b = engine_for(g), engine_for(g)
+    a.kubo_create_particles(300, seed=21)
+    b.kubo_create_particles(300, seed=21)
+    state = b.particles()
+    ma = a.kubo_step(g.dt, 40)
+    mb = b.kubo_step_host_state(g.dt, 40, state)
+    pa = a.particles()
+    assert all(np.array_equal(pa[k], state[k]) for k in pa)
+    assert np.allclose(ma, mb, rtol=1e-13, atol=0)
+
+
+def test_population_split_over_handles_gives_same_trajectories(golden_small):
+    """Exciton streams are keyed by global id: two half-populations == one whole (the multi-GPU sharding rule)."""
+    g = golden_small
+    whole = engine_for(g)
+    whole.kubo_create_particles(200, seed=8, first_global_id=0)
+    whole.kubo_step(g.dt, 80, want_msd=False)
+    pw = whole.particles()
+    parts = []
+    for first in (0, 100):
+        e = engine_for(g)
+        e.kubo_create_particles(100, seed=8, first_global_id=first)
+        e.kubo_step(g.dt, 80, want_msd=False)
+        parts.append(e.particles())
+    for k in pw:
+        assert np.array_equal(pw[k], np.concatenate([p[k] for p in parts], axis=-1)), k
+
+
+def test_c2_size_table_against_oracle():
+    """BASELINE config 2's film (1000 tubes x 100 sites): 3.08e6 CSR entries, all bit-identical to the oracle."""
+    pos, ori = film.film(**film.CONFIG_FILMS["C2"])
+    mc = base_mc()
+    e = Engine(mc)
+    e.set_mesh(pos, ori)
+    e.kubo_init()
+    t = T1m.T1()
+    t.kubo_init(mc, pos, ori)
+    for a, b in zip(e.csr(), t.csr()):
+        assert np.array_equal(a, b)
+    se, st = e.sites(), t.sites()
+    assert np.array_equal(se["max_rate"], st["max_rate"]) and np.array_equal(se["inv_max_rate"], st["inv_max_rate"])
+    assert e.csr_midpoint_guards() == 0
+    # 20 000 excitons, 30 steps: site of every exciton identical to the oracle (memoised rows)
+    t.set_memo(True)
+    t.draws_philox(1)
+    t.create_particles(20000)
+    t.kubo_step(1e-13, 30, want_msd=False)
+    e.kubo_create_particles(20000, seed=1)
+    e.kubo_step(1e-13, 30, want_msd=False)
+    pe, pt = e.particles(), t.particles()
+    assert np.array_equal(pe["site"], pt["site"])
+    assert np.allclose(pe["delta"], pt["delta"], rtol=1e-9, atol=1e-18)
+    assert e.hops() == t.hops()
+
+
+def test_isolated_site_is_an_error_not_garbage():
+    pos, ori = film.film(NT=3, NP=1, a=5.0, LX=500.0, LY=300.0, seed=2)  # three far-apart single-site "tubes"
+    e = Engine(base_mc())
+    e.set_mesh(pos, ori)
+    with pytest.raises(CntmcError) as ei:
+        e.kubo_init()
+    assert ei.value.code == -3 and "no neighbour" in str(ei.value)

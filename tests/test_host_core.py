@@ -1,0 +1,108 @@
+"""The engine's host/device-shared arithmetic (csrc/hop_core.h, csr_core.h) and host set-up (host_setup.cpp), compiled
+for the CPU by tests/host_emul, against the golden vectors and the oracle.  This is the code the CUDA kernels inline;
+the GPU tests (-m gpu) repeat these checks through the real kernels."""
+import numpy as np
+import pytest
+
+from emul import Emul
+from oracle import t1 as T1m
+from cnt_film_monte_carlo_b200 import film
+from conftest import base_mc
+
+STATE_KEYS = ("site", "pos", "delta", "ff", "heading")
+
+
+def test_setup_and_neighbour_table(golden):
+    e = Emul(golden.mc)
+    e.kubo_init(golden.pos_nm, golden.orient)
+    sites = e.sites()
+    for k, v in golden.group("site_").items():
+        assert np.array_equal(sites[k], v), k  # includes the closed-form trim permutation and Gamma_i, 1/Gamma_i
+    dom, rem = e.domains()
+    assert np.array_equal(dom, golden.z["domain"]) and np.array_equal(rem, golden.z["removal"])
+    assert np.array_equal(e.inject(), golden.z["inject"])
+    rp, nbr, cum = e.csr()
+    assert np.array_equal(rp, golden.z["row_ptr"]) and np.array_equal(nbr, golden.z["nbr"])
+    assert np.array_equal(cum, golden.z["cum"])
+    assert np.array_equal(e.table_rates(golden.z["table_rates"].size), golden.z["table_rates"].ravel())
+    assert e.guards() == 0
+
+
+def test_replay_is_bit_exact(golden):
+    e = Emul(golden.mc)
+    e.kubo_init(golden.pos_nm, golden.orient)
+    e.create_replay(golden.z["draw_off"], golden.z["draws"], golden.z["draw_logs"])
+    p0 = e.particles()
+    for k in ("site", "pos", "ff", "heading"):
+        assert np.array_equal(p0[k], golden.z["p0_" + k]), k
+    msd = e.kubo_step(golden.dt, golden.nsteps)
+    p1 = e.particles()
+    for k in STATE_KEYS:
+        assert np.array_equal(p1[k], golden.z["p1_" + k]), k
+    assert np.array_equal(p1["ndraw"], np.diff(golden.z["draw_off"]))  # every recorded draw consumed, none missing
+    assert np.allclose(msd, golden.z["msd"], rtol=1e-13, atol=0)
+
+
+def test_step_subdivision_is_exact(golden_small):
+    """Running the steps one call at a time changes nothing (state carries everything)."""
+    g = golden_small
+    a, b = Emul(g.mc), Emul(g.mc)
+    for e in (a, b):
+        e.kubo_init(g.pos_nm, g.orient)
+        e.create_philox(40, seed=9)
+    a.kubo_step(g.dt, 60)
+    for _ in range(60):
+        b.kubo_step(g.dt, 1)
+    pa, pb = a.particles(), b.particles()
+    assert all(np.array_equal(pa[k], pb[k]) for k in pa)
+
+
+def test_philox_matches_oracle_with_site_sequences(golden):
+    e = Emul(golden.mc)
+    e.kubo_init(golden.pos_nm, golden.orient)
+    e.create_philox(64, seed=12345, first_gid=1000)
+    msd = e.kubo_step(golden.dt, 150, trace_cap=1 << 14)
+    t = T1m.T1()
+    t.kubo_init(golden.mc, golden.pos_nm, golden.orient)
+    t.draws_philox(12345)
+    t.trace_sites(True)
+    t.create_particles(64, first_global_id=1000)
+    msd_t = t.kubo_step(golden.dt, 150)
+    pe, pt = e.particles(), t.particles()
+    for k in STATE_KEYS:
+        assert np.array_equal(pe[k], pt[k]), k
+    off_t, flat_t = t.traced_sites(1064)
+    off_e, flat_e = e.trace()
+    assert np.array_equal(np.diff(off_t)[1000:], np.diff(off_e)) and np.array_equal(flat_t, flat_e)
+    assert e.hops() == t.hops() and len(flat_e) == e.hops()
+    assert np.allclose(msd, msd_t, rtol=1e-13, atol=0)
+
+
+def test_select_entry_equals_reference_loop():
+    e = Emul(base_mc())
+    rng = np.random.default_rng(11)
+    for _ in range(3000):
+        d = int(rng.integers(1, 120))
+        c = np.cumsum(rng.random(d) * (rng.random(d) > 0.25))
+        for dice in (0.0, c[-1], c[-1] * rng.random(), float(rng.choice(c)), np.nextafter(float(rng.choice(c)), 0)):
+            assert e.select(c, dice) == T1m.select(c, dice)
+
+
+def test_untrimmed_bigger_film_against_oracle():
+    pos, ori = film.film(NT=120, NP=60, a=5.0, LX=300.0, LY=80.0, seed=5)
+    mc = base_mc()
+    e = Emul(mc)
+    e.kubo_init(pos, ori)
+    t = T1m.T1()
+    t.kubo_init(mc, pos, ori)
+    for a, b in zip(e.csr(), t.csr()):
+        assert np.array_equal(a, b)
+    t.set_memo(True)
+    t.draws_philox(3)
+    t.create_particles(500)
+    t.kubo_step(1e-13, 50, want_msd=False)
+    e.create_philox(500, seed=3)
+    e.kubo_step(1e-13, 50)
+    pe, pt = e.particles(), t.particles()
+    for k in STATE_KEYS:
+        assert np.array_equal(pe[k], pt[k]), k
