@@ -160,12 +160,16 @@ __global__ void __launch_bounds__(128) kubo_flat_kernel(const KuboArgs a) {
   Draws         D{};
   Cursor        c{};
   int32_t*      trace = nullptr;
+  int32_t       trace_base = 0;
   if (active) {
     load_lane(L, a.S, a.T, e);
     init_draws(D, a.draws, a.S, e);
     c.step = 0;
     begin_step(c, L, a.dt);
-    if (a.trace_sites) trace = a.trace_sites + e * (int64_t)a.trace_cap;
+    if (a.trace_sites) {  // the trace continues where the previous launch stopped
+      trace_base = a.trace_counts[e];
+      trace = a.trace_sites + e * (int64_t)a.trace_cap + trace_base;
+    }
   } else {
     c.step = a.nsteps;
   }
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(128) kubo_flat_kernel(const KuboArgs a) {
     const bool running = c.step < a.nsteps;
     if (!__any_sync(kFullMask, running)) break;
     bool ended = false;
-    if (running) ended = advance(L, a.T, D, c, trace, (uint32_t)a.trace_cap);
+    if (running) ended = advance(L, a.T, D, c, trace, (uint32_t)(a.trace_cap - trace_base));
     unsigned m = __ballot_sync(kFullMask, ended);
     while (m) {
       const int      s0 = __shfl_sync(kFullMask, c.step, __ffs(m) - 1);
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(128) kubo_flat_kernel(const KuboArgs a) {
 
   if (active) {
     store_lane(L, a.S, e);
-    if (a.trace_counts) a.trace_counts[e] = (int32_t)L.nevent;
+    if (a.trace_counts) a.trace_counts[e] = trace_base + (int32_t)L.nevent;
     if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
     if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
     if (L.nreinject) atomicAdd(a.counters + CTR_REINJECT, (unsigned long long)L.nreinject);
