@@ -177,7 +177,7 @@ def run_ours(args, rank, world, local_rank):
     pos, ori = film.film(**film.CONFIG_FILMS["C2"])
     eng = Engine(mc_block(P), device=local_rank, stream=stream.cuda_stream)
     eng.set_mesh(pos, ori)
-    for k, v in (("chunk_steps", args.chunk), ("sort", args.sort), ("block", args.block)):
+    for k, v in (("chunk_steps", args.chunk), ("sort", args.sort), ("occupancy", args.occupancy)):
         eng.set_option(k, v)
     eng.kubo_init()
     eng.kubo_create_particles(P, seed=1, first_global_id=rank * P)
@@ -289,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "excitons_per_gpu": P, "dt_s": DT, "intervals_per_step": n_int,
                        "hops_per_step": hops_total / args.steps, "l2": "flushed between timed steps (256 MiB fill, outside the events)",
-                       "chunk_steps": args.chunk, "sort": args.sort, "block": args.block,
+                       "chunk_steps": args.chunk, "sort": args.sort, "occupancy": args.occupancy,
                        "parallelism": "exciton sharding x%d, tables replicated, 1 all-reduce/step" % world,
                        "msd_last_m2": msd_last},
             "clocks": clocks,
@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--intervals", type=int, default=100, help="sampling intervals (dt = 1e-13 s) per bench step")
     ap.add_argument("--chunk", type=int, default=64)
     ap.add_argument("--sort", type=int, default=1)
-    ap.add_argument("--block", type=int, default=128)
+    ap.add_argument("--occupancy", type=int, default=6, help="resident 128-thread blocks per SM of the hop kernel (4, 5, 6, 8)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-excitons", type=int, default=8000)
     ap.add_argument("--cpu-intervals", type=int, default=400)

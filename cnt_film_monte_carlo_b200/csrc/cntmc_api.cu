@@ -102,8 +102,7 @@ struct cntmc_handle {
   double                csr_seconds = 0;
 
   // device tables
-  DevBuf<FlyRec>  d_fly;
-  DevBuf<HopRec>  d_hop;
+  DevBuf<SiteRec> d_site;
   DevBuf<double>  d_cum;
   DevBuf<int32_t> d_nbr, d_inject, d_c1, d_c2;
   DevBuf<double>  d_theta, d_z, d_a1, d_a2, d_rates;
@@ -125,7 +124,8 @@ struct cntmc_handle {
   DevBuf<double>   r_logs;
 
   // reductions, diagnostics
-  DevBuf<double>             d_partial, d_sums;
+  DevBuf<double>             d_partial, d_sums, d_stage;
+  DevBuf<uint32_t>           d_stage_ev;
   DevBuf<int32_t>            d_flags;
   DevBuf<unsigned long long> d_counters;
   DevBuf<int32_t>            d_trace_sites, d_trace_counts;
@@ -139,6 +139,9 @@ struct cntmc_handle {
   int64_t opt_chunk = 64;   // time steps per launch
   int64_t opt_sort = 1;     // regroup excitons by activity between launches
   int64_t opt_block = 128;  // threads per block of the hop kernel
+  int64_t opt_occupancy = 6;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
+  int64_t opt_stage_mb = 4096;  // cap on the (step, exciton) staging buffer; shortens the launches if needed
+  int     sm_count = 0;
   int64_t opt_time_kernels = 0;  // CUDA events around every hop-kernel launch (bench.py's roofline figure)
   std::vector<cudaEvent_t> kernel_events;
   double  kernel_ms = 0;
@@ -157,9 +160,6 @@ struct cntmc_handle {
     S.px = e_px.p; S.py = e_py.p; S.pz = e_pz.p;
     S.dx = e_dx.p; S.dy = e_dy.p; S.dz = e_dz.p;
     S.ff = e_ff.p;
-    S.ox = contact_mode ? e_ox.p : nullptr;
-    S.oy = contact_mode ? e_oy.p : nullptr;
-    S.oz = contact_mode ? e_oz.p : nullptr;
     S.site = e_site.p;
     S.heading = e_heading.p;
     S.ndraw = e_ndraw.p;
@@ -249,15 +249,11 @@ void common_init(cntmc_t* h) {
 
   // site geometry in site order and in bucket order
   std::vector<SiteGeom> geom((size_t)N), cell_geom((size_t)N);
-  std::vector<FlyRec>   fly((size_t)N);
+  const std::vector<SiteRec> rec = make_site_records(h->sites, h->prm.velocity);
   for (int64_t i = 0; i < N; ++i) {
     SiteGeom& g = geom[(size_t)i];
     g.px = h->sites.pos[0][(size_t)i]; g.py = h->sites.pos[1][(size_t)i]; g.pz = h->sites.pos[2][(size_t)i];
     g.ox = h->sites.orient[0][(size_t)i]; g.oy = h->sites.orient[1][(size_t)i]; g.oz = h->sites.orient[2][(size_t)i];
-    FlyRec& f = fly[(size_t)i];
-    f.x = g.px; f.y = g.py; f.z = g.pz;
-    f.left = h->sites.left[(size_t)i];
-    f.right = h->sites.right[(size_t)i];
   }
   for (int64_t q = 0; q < N; ++q) cell_geom[(size_t)q] = geom[(size_t)h->buckets.sites[(size_t)q]];
   DevBuf<SiteGeom> d_geom, d_cell_geom;
@@ -270,8 +266,7 @@ void common_init(cntmc_t* h) {
   d_cell_sites.upload(h->buckets.sites, st);
   d_cell_start.upload(h->buckets.start, st);
   d_deg.alloc((size_t)N);
-  h->d_fly.upload(fly, st);
-  h->d_hop.alloc((size_t)N);
+  h->d_site.upload(rec, st);
 
   CsrArgs a{};
   a.geom = d_geom.p;
@@ -288,7 +283,7 @@ void common_init(cntmc_t* h) {
   a.R.n_theta = (int32_t)t.theta.size(); a.R.n_z = (int32_t)t.z.size();
   a.R.n_a1 = (int32_t)t.a1.size(); a.R.n_a2 = (int32_t)t.a2.size();
   a.deg = d_deg.p;
-  a.hop = h->d_hop.p;
+  a.site = h->d_site.p;
   a.flags = h->d_flags.p;
   a.counters = h->d_counters.p;
 
@@ -317,8 +312,8 @@ void common_init(cntmc_t* h) {
   unsigned long long ctrs[CTR_COUNT];
   h->d_flags.download(flags, FLAG_COUNT, st);
   h->d_counters.download(ctrs, CTR_COUNT, st);
-  std::vector<HopRec> hop((size_t)N);
-  h->d_hop.download(hop.data(), (size_t)N, st);
+  std::vector<SiteRec> hop((size_t)N);
+  h->d_site.download(hop.data(), (size_t)N, st);
   CUDA_CHECK(cudaStreamSynchronize(st));
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -330,11 +325,10 @@ void common_init(cntmc_t* h) {
   h->inv_max_rate.resize((size_t)N);
   for (int64_t i = 0; i < N; ++i) {
     h->max_rate[(size_t)i] = hop[(size_t)i].total;
-    h->inv_max_rate[(size_t)i] = hop[(size_t)i].inv_total;
+    h->inv_max_rate[(size_t)i] = 1. / hop[(size_t)i].total;  // scatterer.h:92
   }
 
-  h->T.fly = h->d_fly.p;
-  h->T.hop = h->d_hop.p;
+  h->T.site = h->d_site.p;
   h->T.cum = h->d_cum.p;
   h->T.nbr = h->d_nbr.p;
   h->T.velocity = h->prm.velocity;
@@ -377,24 +371,46 @@ void create_common(cntmc_t* h, int64_t P) {
   check_flags(h);
 }
 
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+
+template <typename Draws>
+void launch_kubo(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) {
+  switch (h->opt_occupancy) {
+    case 4: kubo_kernel<Draws, 4><<<grid, 128, 0, st>>>(a); break;
+    case 5: kubo_kernel<Draws, 5><<<grid, 128, 0, st>>>(a); break;
+    case 8: kubo_kernel<Draws, 8><<<grid, 128, 0, st>>>(a); break;
+    default: kubo_kernel<Draws, 6><<<grid, 128, 0, st>>>(a); break;
+  }
+}
+
 // nsteps x kubo_step on the device; sums -> dev_sums[nsteps][4]
 void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   require(h->initialised && !h->contact_mode, "call cntmc_kubo_init first");
   require(h->P > 0, "no excitons: call cntmc_kubo_create_particles first");
   require(nsteps > 0, "nsteps must be positive");
   use_device(h);
-  cudaStream_t  st = h->stream;
-  const int     block = (int)h->opt_block;
-  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->opt_chunk, 256));
-  const unsigned grid = (unsigned)((h->P + block - 1) / block);
-  h->d_partial.alloc((size_t)grid * (size_t)std::min(chunk, nsteps) * 4);
+  cudaStream_t st = h->stream;
+  if (h->sm_count == 0) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // time steps per launch: the option, capped so that the (step, exciton) staging buffer stays within its budget
+  const int64_t by_budget = std::max<int64_t>(1, (h->opt_stage_mb << 20) / (28 * h->P));
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({h->opt_chunk, by_budget, nsteps}));
+  // persistent grid: as many 128-thread blocks as the SMs hold at the compiled occupancy, never more than needed
+  const int64_t  want = (h->P + 127) / 128;
+  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)h->sm_count * h->opt_occupancy);
+  h->d_stage.alloc((size_t)3 * (size_t)chunk * (size_t)h->P);
+  h->d_stage_ev.alloc((size_t)chunk * (size_t)h->P);
+  h->d_partial.alloc((size_t)chunk * kStageSplits * 4);
   h->last_launches = 0;
   CUDA_CHECK(cudaEventRecord(h->ev0, st));
   for (int64_t done = 0; done < nsteps; done += chunk) {
-    const int n = (int)std::min(chunk, nsteps - done);
-    const uint32_t* perm = nullptr;
-    if (h->opt_sort && h->have_events && h->trace_cap == 0) {
-      // heaviest excitons first, excitons of similar activity share a warp
+    const int       n = (int)std::min(chunk, nsteps - done);
+    const uint32_t* order = nullptr;
+    if (h->opt_sort && h->have_events) {
+      // queue order: most active excitons (events in the previous launch) first
       iota_kernel<<<(unsigned)((h->P + 255) / 256), 256, 0, st>>>(h->e_iota.p, h->P);
       size_t bytes = 0;
       cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->e_events.p, h->e_keys_out.p, h->e_iota.p, h->e_perm.p,
@@ -402,24 +418,25 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
       h->sort_tmp.alloc(bytes);
       CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp.p, bytes, h->e_events.p, h->e_keys_out.p, h->e_iota.p,
                                                            h->e_perm.p, (int)h->P, 0, 32, st));
-      perm = h->e_perm.p;
-      h->last_launches += 2;
+      order = h->e_perm.p;
+      h->last_launches += 1;
     }
+    set_u64_kernel<<<1, 1, 0, st>>>(h->d_counters.p + CTR_QUEUE, (unsigned long long)grid * 128ull);
     KuboArgs a{};
     a.T = h->T;
     a.S = h->arrays();
     a.draws = h->draws;
-    a.perm = perm;
+    a.order = order;
     a.P = h->P;
     a.dt = dt;
     a.nsteps = n;
-    a.partial = h->d_partial.p;
+    a.stage = h->d_stage.p;
+    a.stage_ev = h->d_stage_ev.p;
     a.trace_sites = h->trace_cap ? h->d_trace_sites.p : nullptr;
     a.trace_counts = h->trace_cap ? h->d_trace_counts.p : nullptr;
     a.trace_cap = h->trace_cap;
     a.flags = h->d_flags.p;
     a.counters = h->d_counters.p;
-    const size_t smem = (size_t)(block / 32) * n * 4 * sizeof(double);
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     if (h->opt_time_kernels) {
       CUDA_CHECK(cudaEventCreate(&k0));
@@ -429,14 +446,16 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
       CUDA_CHECK(cudaEventRecord(k0, st));
     }
     if (h->replay)
-      kubo_flat_kernel<ReplayDraws><<<grid, block, smem, st>>>(a);
+      launch_kubo<ReplayDraws>(h, a, grid, st);
     else
-      kubo_flat_kernel<PhiloxDraws><<<grid, block, smem, st>>>(a);
+      launch_kubo<PhiloxDraws>(h, a, grid, st);
     CUDA_CHECK(cudaGetLastError());
     if (k1) CUDA_CHECK(cudaEventRecord(k1, st));
-    reduce_partials_kernel<<<n, 128, 0, st>>>(h->d_partial.p, (int)grid, n, dev_sums + done * 4);
+    reduce_stage_kernel<<<dim3((unsigned)n, kStageSplits), 256, 0, st>>>(h->d_stage.p, h->d_stage_ev.p, h->P, n, h->d_partial.p);
     CUDA_CHECK(cudaGetLastError());
-    h->last_launches += 2;
+    finish_sums_kernel<<<(n * 4 + 127) / 128, 128, 0, st>>>(h->d_partial.p, n, dev_sums + done * 4);
+    CUDA_CHECK(cudaGetLastError());
+    h->last_launches += 4;
     h->have_events = true;
   }
   CUDA_CHECK(cudaEventRecord(h->ev1, st));
@@ -854,6 +873,12 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "block") {
       require(value == 32 || value == 64 || value == 128, "block must be 32, 64 or 128");
       h->opt_block = value;
+    } else if (k == "occupancy") {
+      require(value == 4 || value == 5 || value == 6 || value == 8, "occupancy must be 4, 5, 6 or 8 blocks per SM");
+      h->opt_occupancy = value;
+    } else if (k == "stage_mb") {
+      require(value >= 1, "stage_mb must be positive");
+      h->opt_stage_mb = value;
     } else if (k == "time_kernels") {
       h->opt_time_kernels = value ? 1 : 0;
     } else {
@@ -866,6 +891,8 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "chunk_steps") return h->opt_chunk;
   if (k == "sort") return h->opt_sort;
   if (k == "block") return h->opt_block;
+  if (k == "occupancy") return h->opt_occupancy;
+  if (k == "stage_mb") return h->opt_stage_mb;
   return -1;
 }
 double  cntmc_last_step_ms(const cntmc_t* h) { return h->last_ms; }

@@ -83,3 +83,11 @@ std::vector<int32_t> contact_sites(const Sites& s, const Domain& d, int n_seg, i
 std::vector<int32_t> slab_sites_half_open(const Sites& s, const Domain& d, int n_seg, int i);  // monte_carlo.h:296-301
 
 }  // namespace cntmc
+
+// ---- device-table records built on the host --------------------------------------------------------------------------
+#include "hop_core.h"
+namespace cntmc {
+// position, links and the two segment flight times of every site (hop_core.h SiteRec quarters 0-2); quarter 3 (total
+// rate and CSR row) is filled by the neighbour-table kernel.
+std::vector<SiteRec> make_site_records(const Sites& s, double velocity);
+}  // namespace cntmc

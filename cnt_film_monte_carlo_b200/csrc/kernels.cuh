@@ -1,12 +1,13 @@
 // kernels.cuh -- the CUDA kernels of the hop path (sm_100a).
 //
-//   K1  count_rows_kernel / fill_rows_kernel   neighbour table: scatterer::find_neighbors of every site, once, as CSR
-//   K4  create_excitons_kernel                 monte_carlo::kubo_create_particles / create_particles / repopulate
-//   K2  kubo_flat_kernel                       nsteps x monte_carlo::kubo_step for every exciton + per-step sum of dx^2
-//       reduce_partials_kernel                 block partials -> [nsteps][4] sums, fixed order (deterministic)
+//   K1  csr_rows_kernel<false/true>   neighbour table: scatterer::find_neighbors of every site, once, as CSR
+//   K4  create_excitons_kernel        monte_carlo::kubo_create_particles / create_particles / repopulate
+//   K2  kubo_kernel                   nsteps x monte_carlo::kubo_step for every exciton (persistent warps, lanes refill)
+//       reduce_stage_kernel           per-(step, exciton) squared displacements -> [nsteps][4] sums, fixed order
 //
 // All arithmetic is FP64 / integer; there is no dense contraction anywhere on this path, so tensor cores (tcgen05)
-// do not apply.  The kernels are bound by dependent gathers into the L2-resident site and CSR tables.
+// do not apply.  The kernels are bound by instruction issue and by dependent gathers into the L2-resident site and CSR
+// tables (DESIGN.md has the measurements).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,12 +22,11 @@ struct ExcitonArrays {
   double *  px, *py, *pz;  // particle::_pos
   double *  dx, *dy, *dz;  // particle::_delta_pos
   double*   ff;            // particle::_ff_time
-  double *  ox, *oy, *oz;  // particle::_old_pos (contact mode only; null otherwise)
   int32_t*  site;          // particle::_scat_ptr
   uint8_t*  heading;       // particle::_heading_right
   uint32_t* ndraw;         // next draw index of the exciton's stream
   uint32_t* last_events;   // events in the previous launch (load-balancing key)
-  uint64_t* gid;           // stream id (contact mode, where excitons are created and destroyed); null = first_gid + index
+  uint64_t* gid;           // stream id where excitons are created and destroyed (contact mode); null = first_gid + index
 };
 
 struct DrawConfig {
@@ -49,13 +49,8 @@ __device__ __forceinline__ void load_lane(Lane& L, const ExcitonArrays& S, const
   L.heading_right = S.heading[e] != 0;
   L.ndraw = S.ndraw[e];
   L.nevent = 0;
-  L.nreinject = 0;
-  L.ncross = 0;
-  L.nprobe = 0;
   L.stuck = false;
-  const FlyRec f = load_fly(T.fly + L.site);
-  L.left = f.left;
-  L.right = f.right;
+  attach_site(L, T);
 }
 __device__ __forceinline__ void store_lane(const Lane& L, const ExcitonArrays& S, int64_t e) {
   S.px[e] = L.px;
@@ -84,7 +79,9 @@ __device__ __forceinline__ void init_draws<ReplayDraws>(ReplayDraws& D, const Dr
 }
 
 enum { FLAG_STUCK = 0, FLAG_REPLAY = 1, FLAG_EMPTY_ROW = 2, FLAG_COUNT = 4 };
-enum { CTR_REINJECT = 0, CTR_GUARD = 1, CTR_CROSS = 2, CTR_PROBE = 3, CTR_COUNT = 4 };
+enum { CTR_REINJECT = 0, CTR_GUARD = 1, CTR_CROSS = 2, CTR_PROBE = 3, CTR_QUEUE = 4, CTR_COUNT = 8 };
+
+constexpr unsigned kFullMask = 0xffffffffu;
 
 // ---- K4: creation ------------------------------------------------------------------------------------------------------
 struct CreateArgs {
@@ -101,68 +98,64 @@ template <typename Draws>
 __global__ void __launch_bounds__(256) create_excitons_kernel(const CreateArgs a) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.P) return;
-  Lane  L;
-  Draws D;
+  Lane  L{};
+  Draws D{};
   init_draws(D, a.draws, a.S, e);
   create_exciton(L, a.T, D, a.site_list, a.n_list);
   store_lane(L, a.S, e);
-  if (a.S.ox) {
-    a.S.ox[e] = L.px;
-    a.S.oy[e] = L.py;
-    a.S.oz[e] = L.pz;
-  }
+  a.S.last_events[e] = 0;
   if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
 }
 
 // ---- K2: the hop kernel, Green-Kubo flavour -------------------------------------------------------------------------------
 struct KuboArgs {
-  Tables          T;
-  ExcitonArrays   S;
-  DrawConfig      draws;
-  const uint32_t* perm;  // thread -> exciton (null = identity); groups excitons of similar activity into warps
-  int64_t         P;
-  double          dt;
-  int32_t         nsteps;
-  double*         partial;  // [gridDim.x][nsteps][4]: sum dx^2, dy^2, dz^2, events
-  int32_t*        trace_sites;
-  int32_t*        trace_counts;
-  int32_t         trace_cap;
-  int32_t*        flags;
+  Tables              T;
+  ExcitonArrays       S;
+  DrawConfig          draws;
+  const uint32_t*     order;  // queue position -> exciton (null = identity); most active excitons first
+  int64_t             P;
+  double              dt;
+  int32_t             nsteps;
+  double*             stage;     // [3][nsteps][P]: dx^2, dy^2, dz^2 of the exciton at queue position q after step s
+  uint32_t*           stage_ev;  // [nsteps][P]: scattering events of that exciton in that step
+  int32_t*            trace_sites;
+  int32_t*            trace_counts;
+  int32_t             trace_cap;
+  int32_t*            flags;
   unsigned long long* counters;
 };
 
-constexpr unsigned kFullMask = 0xffffffffu;
+// Persistent warps; every lane owns one exciton at a time and carries it through all nsteps time steps of the launch,
+// then takes the next unassigned exciton from a global queue (one warp-aggregated atomic).  The queue is ordered by the
+// activity seen in the previous launch, most active first, so the long sequential chains of trapped excitons (thousands
+// of events while the median exciton has two) start at once and the short ones fill in behind them.
+//
+// The loop is flat: an iteration moves every busy lane forward by one scattering event or by the end of one time step,
+// whichever comes first for that lane; lanes of a warp are in general in different time steps of different excitons.
+// Nothing in the loop needs a barrier, shared memory or a floating-point atomic: when a lane ends a step it writes
+// its squared displacement to a (step, queue position) slot, and reduce_stage_kernel sums the slots in a fixed order
+// afterwards, so the ensemble sums do not depend on which lane happened to process which exciton.
+template <typename Draws, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a) {
+  const int      lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int64_t        q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // first assignment is static
+  bool           have = q < a.P;
+  int64_t        e = 0;
+  Lane           L{};
+  Draws          D{};
+  Cursor         c{};
+  int32_t*       trace = nullptr;
+  int32_t        trace_base = 0;
+  const size_t   plane = (size_t)a.nsteps * (size_t)a.P;
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
-  return v;
-}
-
-// One thread per exciton.  The loop is flat: an iteration moves every running lane forward by one scattering event or
-// by the end of one time step, whichever comes first for that lane, so lanes of a warp may be in different time
-// steps.  When lanes finish a step their squared displacements are summed over the lanes that share the step index
-// (shuffle tree with zeros for the others, hence a fixed order) and added to the warp's row for that step in shared
-// memory; nothing in the loop needs a block barrier or an atomic.
-template <typename Draws>
-__global__ void __launch_bounds__(128) kubo_flat_kernel(const KuboArgs a) {
-  extern __shared__ double acc[];  // [warps][nsteps][4]
-  const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int    row = a.nsteps * 4;
-  double*      wacc = acc + (size_t)warp * row;
-  for (int k = lane; k < row; k += 32) wacc[k] = 0.0;
-  __syncwarp();
-
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool    active = t < a.P;
-  const int64_t e = active ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
-  Lane          L{};
-  Draws         D{};
-  Cursor        c{};
-  int32_t*      trace = nullptr;
-  int32_t       trace_base = 0;
-  if (active) {
+  auto take = [&]() {
+    e = a.order ? (int64_t)a.order[q] : q;
+    const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject;
     load_lane(L, a.S, a.T, e);
+    L.ncross = nc;
+    L.nprobe = np;
+    L.nreinject = nr;
     init_draws(D, a.draws, a.S, e);
     c.step = 0;
     begin_step(c, L, a.dt);
@@ -170,86 +163,90 @@ __global__ void __launch_bounds__(128) kubo_flat_kernel(const KuboArgs a) {
       trace_base = a.trace_counts[e];
       trace = a.trace_sites + e * (int64_t)a.trace_cap + trace_base;
     }
-  } else {
-    c.step = a.nsteps;
-  }
+  };
+  if (have) take();
 
-  for (;;) {
-    const bool running = c.step < a.nsteps;
-    if (!__any_sync(kFullMask, running)) break;
-    bool ended = false;
-    if (running) ended = advance(L, a.T, D, c, trace, (uint32_t)(a.trace_cap - trace_base));
-    unsigned m = __ballot_sync(kFullMask, ended);
-    while (m) {
-      const int      s0 = __shfl_sync(kFullMask, c.step, __ffs(m) - 1);
-      const bool     mine = ended && (c.step == s0);
-      const unsigned grp = __ballot_sync(kFullMask, mine);
-      const double   sx = warp_sum(mine ? L.dx * L.dx : 0.0);
-      const double   sy = warp_sum(mine ? L.dy * L.dy : 0.0);
-      const double   sz = warp_sum(mine ? L.dz * L.dz : 0.0);
-      const int      ev = __reduce_add_sync(kFullMask, mine ? (int)(L.nevent - c.ev0) : 0);
-      if (lane == 0) {
-        double* r = wacc + s0 * 4;
-        r[0] += sx;
-        r[1] += sy;
-        r[2] += sz;
-        r[3] += (double)ev;
+  while (__any_sync(kFullMask, have)) {
+    bool finished = false;
+    if (have) {
+      if (advance(L, a.T, D, c, trace, (uint32_t)(a.trace_cap - trace_base))) {
+        const size_t slot = (size_t)c.step * (size_t)a.P + (size_t)q;
+        a.stage[slot] = L.dx * L.dx;  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
+        a.stage[plane + slot] = L.dy * L.dy;
+        a.stage[2 * plane + slot] = L.dz * L.dz;
+        a.stage_ev[slot] = L.nevent - c.ev0;
+        ++c.step;
+        begin_step(c, L, a.dt);
       }
-      m &= ~grp;
+      finished = (c.step >= a.nsteps) || L.stuck;
     }
-    if (ended) {
-      ++c.step;
-      begin_step(c, L, a.dt);
+    const unsigned fm = __ballot_sync(kFullMask, finished);
+    if (fm) {
+      if (finished) {
+        store_lane(L, a.S, e);
+        if (a.trace_counts) a.trace_counts[e] = trace_base + (int32_t)L.nevent;
+        if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
+        if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
+      }
+      unsigned long long base = 0;
+      const int          leader = __ffs(fm) - 1;
+      if (lane == leader) base = atomicAdd(a.counters + CTR_QUEUE, (unsigned long long)__popc(fm));
+      base = __shfl_sync(kFullMask, base, leader);
+      if (finished) {
+        q = (int64_t)base + __popc(fm & lt_mask);
+        have = q < a.P;
+        if (have) take();
+      }
     }
-    if (L.stuck) c.step = a.nsteps;  // give up on this lane; the host reports the error
   }
 
-  if (active) {
-    store_lane(L, a.S, e);
-    if (a.trace_counts) a.trace_counts[e] = trace_base + (int32_t)L.nevent;
-    if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
-    if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
-    if (L.nreinject) atomicAdd(a.counters + CTR_REINJECT, (unsigned long long)L.nreinject);
-  }
-  {
-    const unsigned nc = __reduce_add_sync(kFullMask, active ? L.ncross : 0u);
-    const unsigned np = __reduce_add_sync(kFullMask, active ? L.nprobe : 0u);
-    if (lane == 0) {
-      atomicAdd(a.counters + CTR_CROSS, (unsigned long long)nc);
-      atomicAdd(a.counters + CTR_PROBE, (unsigned long long)np);
-    }
-  }
-  __syncthreads();
-  double* out = a.partial + (size_t)blockIdx.x * row;
-  for (int k = threadIdx.x; k < row; k += blockDim.x) {
-    double s = 0.0;
-    for (int w = 0; w < nwarps; ++w) s += acc[(size_t)w * row + k];
-    out[k] = s;
+  const unsigned nc = __reduce_add_sync(kFullMask, L.ncross);
+  const unsigned np = __reduce_add_sync(kFullMask, L.nprobe);
+  const unsigned nr = __reduce_add_sync(kFullMask, L.nreinject);
+  if (lane == 0) {
+    if (nc) atomicAdd(a.counters + CTR_CROSS, (unsigned long long)nc);
+    if (np) atomicAdd(a.counters + CTR_PROBE, (unsigned long long)np);
+    if (nr) atomicAdd(a.counters + CTR_REINJECT, (unsigned long long)nr);
   }
 }
 
-// sums[s][c] = sum over blocks of partial[b][s][c], in a fixed order: thread j adds blocks j, j+T, j+2T, ... then a
-// shared-memory tree.  One block per time step.
-__global__ void __launch_bounds__(128) reduce_partials_kernel(const double* partial, int nblocks, int nsteps, double* sums) {
-  __shared__ double sh[128][4];
-  const int         s = blockIdx.x;
+// partial[s][j][c] = sum over the j-th slice of queue positions of stage[c][s][q] (c = 3: events), thread-strided then
+// a shared-memory tree: the order is fixed by (P, kStageSplits) alone.
+constexpr int kStageSplits = 16;
+__global__ void __launch_bounds__(256) reduce_stage_kernel(const double* stage, const uint32_t* stage_ev, int64_t P, int nsteps,
+                                                           double* partial) {
+  __shared__ double sh[256][4];
+  const int         s = blockIdx.x, j = blockIdx.y;
+  const int64_t     len = (P + kStageSplits - 1) / kStageSplits;
+  const int64_t     q0 = (int64_t)j * len, q1 = (q0 + len < P) ? q0 + len : P;
+  const size_t      plane = (size_t)nsteps * (size_t)P;
+  const size_t      row = (size_t)s * (size_t)P;
   double            v[4] = {0, 0, 0, 0};
-  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
-    const double* p = partial + ((size_t)b * nsteps + s) * 4;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) v[c] += p[c];
+  for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+    v[0] += stage[row + q];
+    v[1] += stage[plane + row + q];
+    v[2] += stage[2 * plane + row + q];
+    v[3] += (double)stage_ev[row + q];
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) sh[threadIdx.x][c] = v[c];
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
+  for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) sh[threadIdx.x][c] += sh[threadIdx.x + o][c];
     }
     __syncthreads();
   }
-  if (threadIdx.x < 4) sums[(size_t)s * 4 + threadIdx.x] = sh[0][threadIdx.x];
+  if (threadIdx.x < 4) partial[((size_t)s * kStageSplits + j) * 4 + threadIdx.x] = sh[0][threadIdx.x];
+}
+__global__ void finish_sums_kernel(const double* partial, int nsteps, double* sums) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nsteps * 4) return;
+  const int s = k >> 2, c = k & 3;
+  double    v = 0.0;
+  for (int j = 0; j < kStageSplits; ++j) v += partial[((size_t)s * kStageSplits + j) * 4 + c];
+  sums[k] = v;
 }
 
 __global__ void iota_kernel(uint32_t* v, int64_t n) {
@@ -273,7 +270,7 @@ struct CsrArgs {
   const uint64_t* row_begin;  // [N+1]    (fill pass; exclusive scan of deg)
   int32_t*        nbr;
   double*         cum;
-  HopRec*         hop;
+  SiteRec*        site;       // quarter 3 of every record: total rate and CSR row
   int32_t*        flags;
   unsigned long long* counters;
 };
@@ -313,13 +310,9 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
   if (!kFill) {
     a.deg[i] = d;
   } else {
-    HopRec h;
-    h.total = acc;                    // scatterer.h:91  _max_rate = neighbors.back().first
-    h.inv_total = (d ? 1. / acc : 0.0);  // scatterer.h:92
-    h.row_begin = (uint32_t)base;
-    h.row_len = d;
-    h.pad[0] = h.pad[1] = 0;
-    a.hop[i] = h;
+    a.site[i].total = acc;  // scatterer.h:91  _max_rate = neighbors.back().first
+    a.site[i].row_begin = (uint32_t)base;
+    a.site[i].row_len = d;
     if (d == 0) atomicOr(a.flags + FLAG_EMPTY_ROW, 1);
     if (guard) atomicAdd(a.counters + CTR_GUARD, 1ULL);
   }

@@ -21,8 +21,7 @@ struct Emul {
   Domain               dom;
   Buckets              buckets;
   Injection            inj;
-  std::vector<FlyRec>  fly;
-  std::vector<HopRec>  hop;
+  std::vector<SiteRec> site;
   std::vector<double>  cum;
   std::vector<int32_t> nbr;
   std::vector<int64_t> row_ptr;
@@ -71,14 +70,10 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
     e->inj = injection_region(e->sites, e->dom, e->prm.n_sections);
     const int64_t n = e->sites.N;
     std::vector<SiteGeom> geom((size_t)n);
-    e->fly.resize((size_t)n);
-    e->hop.resize((size_t)n);
+    e->site = make_site_records(e->sites, e->prm.velocity);
     for (int64_t i = 0; i < n; ++i) {
       geom[i] = SiteGeom{e->sites.pos[0][i], e->sites.pos[1][i], e->sites.pos[2][i],
                          e->sites.orient[0][i], e->sites.orient[1][i], e->sites.orient[2][i]};
-      e->fly[i].x = geom[i].px; e->fly[i].y = geom[i].py; e->fly[i].z = geom[i].pz;
-      e->fly[i].left = e->sites.left[i];
-      e->fly[i].right = e->sites.right[i];
     }
     RateTable R{e->table.theta.data(), e->table.z.data(), e->table.a1.data(), e->table.a2.data(), e->table.rates.data(),
                 (int32_t)e->table.theta.size(), (int32_t)e->table.z.size(), (int32_t)e->table.a1.size(), (int32_t)e->table.a2.size()};
@@ -110,14 +105,12 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
             }
           }
       e->row_ptr[i + 1] = e->row_ptr[i] + d;
-      e->hop[i].total = acc;
-      e->hop[i].inv_total = d ? 1. / acc : 0.0;
-      e->hop[i].row_begin = (uint32_t)e->row_ptr[i];
-      e->hop[i].row_len = d;
+      e->site[i].total = acc;
+      e->site[i].row_begin = (uint32_t)e->row_ptr[i];
+      e->site[i].row_len = d;
       e->guards += guard;
     }
-    e->T.fly = e->fly.data();
-    e->T.hop = e->hop.data();
+    e->T.site = e->site.data();
     e->T.cum = e->cum.data();
     e->T.nbr = e->nbr.data();
     e->T.inject = e->inj.sites.data();
@@ -146,8 +139,8 @@ void emul_sites(Emul* e, double* pos, double* orient, int32_t* left, int32_t* ri
   memcpy(left, e->sites.left.data(), N * 4);
   memcpy(right, e->sites.right.data(), N * 4);
   for (size_t i = 0; i < N; ++i) {
-    max_rate[i] = e->hop[i].total;
-    inv[i] = e->hop[i].inv_total;
+    max_rate[i] = e->site[i].total;
+    inv[i] = 1. / e->site[i].total;
   }
 }
 void emul_csr(Emul* e, int64_t* row_ptr, int32_t* nbr, double* cum) {
@@ -262,3 +255,33 @@ void emul_trace(Emul* e, int32_t* flat) {
 }
 int64_t emul_select(const double* cum, int64_t d, double dice) { return (int64_t)select_entry(cum, (uint32_t)d, dice); }
 }  // extern "C"
+
+// ---- scheduling study support: the per-exciton sequence of micro-operations of one launch ----------------------------
+// one int32 per advance() call: (chain crossings << 1) | (1 if the call ended a time step, 0 if it was an event)
+extern "C" int64_t emul_op_sequences(Emul* e, double dt, int64_t nsteps, int64_t* counts, int32_t* flat, int64_t cap) {
+  const int64_t P = (int64_t)e->lanes.size();
+  int64_t       k = 0;
+  for (int64_t i = 0; i < P; ++i) {
+    Lane&       L = e->lanes[i];
+    PhiloxDraws D;
+    Cursor      c;
+    D.init(e->seed, e->first_gid + (uint64_t)i);
+    L.nevent = 0;
+    c.step = 0;
+    begin_step(c, L, dt);
+    int64_t n = 0;
+    while (c.step < nsteps && !L.stuck) {
+      const uint32_t c0 = L.ncross;
+      const bool     ended = advance(L, e->T, D, c, nullptr, 0);
+      if (k < cap) flat[k] = (int32_t)(((L.ncross - c0) << 1) | (ended ? 1 : 0));
+      ++k;
+      ++n;
+      if (ended) {
+        ++c.step;
+        begin_step(c, L, dt);
+      }
+    }
+    counts[i] = n;
+  }
+  return k;
+}

@@ -101,12 +101,12 @@ def test_philox_matches_oracle_site_sequences_and_state(golden):
     assert np.allclose(msd, msd_t, rtol=1e-9, atol=0)
 
 
-def test_chunking_sorting_and_block_size_do_not_change_results():
+def test_chunking_sorting_and_occupancy_do_not_change_results():
     pos, ori = film.film(NT=150, NP=60, a=5.0, LX=300.0, LY=80.0, seed=5)
     mc = base_mc()
     states, msds = [], []
-    for opts in (dict(chunk_steps=64, sort=1, block=128), dict(chunk_steps=7, sort=0, block=64), dict(chunk_steps=1, sort=1, block=32),
-                 dict(chunk_steps=200, sort=1, block=128)):
+    for opts in (dict(chunk_steps=64, sort=1, occupancy=6), dict(chunk_steps=7, sort=0, occupancy=4), dict(chunk_steps=1, sort=1, occupancy=8),
+                 dict(chunk_steps=200, sort=1, occupancy=5), dict(chunk_steps=64, sort=1, stage_mb=1)):
         e = Engine(mc)
         e.set_mesh(pos, ori)
         for k, v in opts.items():
