@@ -103,6 +103,7 @@ struct cntmc_handle {
 
   // device tables
   DevBuf<SiteRec> d_site;
+  DevBuf<PosRec>  d_pos;
   DevBuf<double>  d_cum;
   DevBuf<int32_t> d_nbr, d_inject, d_c1, d_c2;
   DevBuf<double>  d_theta, d_z, d_a1, d_a2, d_rates;
@@ -249,7 +250,8 @@ void common_init(cntmc_t* h) {
 
   // site geometry in site order and in bucket order
   std::vector<SiteGeom> geom((size_t)N), cell_geom((size_t)N);
-  const std::vector<SiteRec> rec = make_site_records(h->sites, h->prm.velocity);
+  std::vector<PosRec>        posrec;
+  const std::vector<SiteRec> rec = make_site_records(h->sites, h->prm.velocity, posrec);
   for (int64_t i = 0; i < N; ++i) {
     SiteGeom& g = geom[(size_t)i];
     g.px = h->sites.pos[0][(size_t)i]; g.py = h->sites.pos[1][(size_t)i]; g.pz = h->sites.pos[2][(size_t)i];
@@ -267,6 +269,7 @@ void common_init(cntmc_t* h) {
   d_cell_start.upload(h->buckets.start, st);
   d_deg.alloc((size_t)N);
   h->d_site.upload(rec, st);
+  h->d_pos.upload(posrec, st);
 
   CsrArgs a{};
   a.geom = d_geom.p;
@@ -325,10 +328,11 @@ void common_init(cntmc_t* h) {
   h->inv_max_rate.resize((size_t)N);
   for (int64_t i = 0; i < N; ++i) {
     h->max_rate[(size_t)i] = hop[(size_t)i].total;
-    h->inv_max_rate[(size_t)i] = 1. / hop[(size_t)i].total;  // scatterer.h:92
+    h->inv_max_rate[(size_t)i] = hop[(size_t)i].inv_total;
   }
 
   h->T.site = h->d_site.p;
+  h->T.pos = h->d_pos.p;
   h->T.cum = h->d_cum.p;
   h->T.nbr = h->d_nbr.p;
   h->T.velocity = h->prm.velocity;

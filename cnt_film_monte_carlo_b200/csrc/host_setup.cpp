@@ -371,22 +371,23 @@ std::vector<int32_t> slab_sites_half_open(const Sites& s, const Domain& d, int n
 }  // namespace cntmc
 
 namespace cntmc {
-std::vector<SiteRec> make_site_records(const Sites& s, double velocity) {
+std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vector<PosRec>& pos) {
   std::vector<SiteRec> rec((size_t)s.N);
+  pos.resize((size_t)s.N);
   for (int64_t i = 0; i < s.N; ++i) {
-    SiteRec& r = rec[(size_t)i];
-    r.x = s.pos[0][(size_t)i];
-    r.y = s.pos[1][(size_t)i];
-    r.z = s.pos[2][(size_t)i];
+    SiteRec&     r = rec[(size_t)i];
+    const double x = s.pos[0][(size_t)i], y = s.pos[1][(size_t)i], z = s.pos[2][(size_t)i];
+    pos[(size_t)i] = PosRec{x, y, z, 0.0};
     r.left = s.left[(size_t)i];
     r.right = s.right[(size_t)i];
     r.q_left = r.q_right = 0.0;
     if (r.left > -1)
-      r.q_left = segment_time(r.x, r.y, r.z, s.pos[0][(size_t)r.left], s.pos[1][(size_t)r.left], s.pos[2][(size_t)r.left], velocity);
+      r.q_left = segment_time(x, y, z, s.pos[0][(size_t)r.left], s.pos[1][(size_t)r.left], s.pos[2][(size_t)r.left], velocity);
     if (r.right > -1)
-      r.q_right = segment_time(r.x, r.y, r.z, s.pos[0][(size_t)r.right], s.pos[1][(size_t)r.right], s.pos[2][(size_t)r.right], velocity);
-    r.total = 0.0;
+      r.q_right = segment_time(x, y, z, s.pos[0][(size_t)r.right], s.pos[1][(size_t)r.right], s.pos[2][(size_t)r.right], velocity);
+    r.total = r.inv_total = 0.0;
     r.row_begin = r.row_len = 0;
+    r.spare[0] = r.spare[1] = r.spare[2] = r.spare[3] = 0;
   }
   return rec;
 }

@@ -87,7 +87,7 @@ std::vector<int32_t> slab_sites_half_open(const Sites& s, const Domain& d, int n
 // ---- device-table records built on the host --------------------------------------------------------------------------
 #include "hop_core.h"
 namespace cntmc {
-// position, links and the two segment flight times of every site (hop_core.h SiteRec quarters 0-2); quarter 3 (total
-// rate and CSR row) is filled by the neighbour-table kernel.
-std::vector<SiteRec> make_site_records(const Sites& s, double velocity);
+// links and the two segment flight times of every site (hop_core.h SiteRec) plus the position records; the rate fields
+// (total, 1/total, CSR row) are filled by the neighbour-table kernel.
+std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vector<PosRec>& pos);
 }  // namespace cntmc

@@ -52,7 +52,7 @@ __device__ __forceinline__ void load_lane(Lane& L, const ExcitonArrays& S, const
   L.stuck = false;
   attach_site(L, T);
 }
-__device__ __forceinline__ void store_lane(const Lane& L, const ExcitonArrays& S, int64_t e) {
+__device__ __forceinline__ void store_lane(const Lane& L, const ExcitonArrays& S, int64_t e) {  // needs L.pos_valid
   S.px[e] = L.px;
   S.py[e] = L.py;
   S.pz[e] = L.pz;
@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
     const unsigned fm = __ballot_sync(kFullMask, finished);
     if (fm) {
       if (finished) {
+        materialize(L, a.T);
         store_lane(L, a.S, e);
         if (a.trace_counts) a.trace_counts[e] = trace_base + (int32_t)L.nevent;
         if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
@@ -270,7 +271,7 @@ struct CsrArgs {
   const uint64_t* row_begin;  // [N+1]    (fill pass; exclusive scan of deg)
   int32_t*        nbr;
   double*         cum;
-  SiteRec*        site;       // quarter 3 of every record: total rate and CSR row
+  SiteRec*        site;       // rate fields of every record: total, 1/total, CSR row
   int32_t*        flags;
   unsigned long long* counters;
 };
@@ -310,7 +311,8 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
   if (!kFill) {
     a.deg[i] = d;
   } else {
-    a.site[i].total = acc;  // scatterer.h:91  _max_rate = neighbors.back().first
+    a.site[i].total = acc;                  // scatterer.h:91  _max_rate = neighbors.back().first
+    a.site[i].inv_total = d ? 1. / acc : 0.0;  // scatterer.h:92
     a.site[i].row_begin = (uint32_t)base;
     a.site[i].row_len = d;
     if (d == 0) atomicOr(a.flags + FLAG_EMPTY_ROW, 1);

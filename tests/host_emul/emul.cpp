@@ -22,6 +22,7 @@ struct Emul {
   Buckets              buckets;
   Injection            inj;
   std::vector<SiteRec> site;
+  std::vector<PosRec>  pos;
   std::vector<double>  cum;
   std::vector<int32_t> nbr;
   std::vector<int64_t> row_ptr;
@@ -70,7 +71,7 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
     e->inj = injection_region(e->sites, e->dom, e->prm.n_sections);
     const int64_t n = e->sites.N;
     std::vector<SiteGeom> geom((size_t)n);
-    e->site = make_site_records(e->sites, e->prm.velocity);
+    e->site = make_site_records(e->sites, e->prm.velocity, e->pos);
     for (int64_t i = 0; i < n; ++i) {
       geom[i] = SiteGeom{e->sites.pos[0][i], e->sites.pos[1][i], e->sites.pos[2][i],
                          e->sites.orient[0][i], e->sites.orient[1][i], e->sites.orient[2][i]};
@@ -106,11 +107,13 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
           }
       e->row_ptr[i + 1] = e->row_ptr[i] + d;
       e->site[i].total = acc;
+      e->site[i].inv_total = d ? 1. / acc : 0.0;
       e->site[i].row_begin = (uint32_t)e->row_ptr[i];
       e->site[i].row_len = d;
       e->guards += guard;
     }
     e->T.site = e->site.data();
+    e->T.pos = e->pos.data();
     e->T.cum = e->cum.data();
     e->T.nbr = e->nbr.data();
     e->T.inject = e->inj.sites.data();
