@@ -387,7 +387,7 @@ std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vec
       r.q_right = segment_time(x, y, z, s.pos[0][(size_t)r.right], s.pos[1][(size_t)r.right], s.pos[2][(size_t)r.right], velocity);
     r.total = r.inv_total = 0.0;
     r.row_begin = r.row_len = 0;
-    r.spare[0] = r.spare[1] = r.spare[2] = r.spare[3] = 0;
+    r.guide[0] = r.guide[1] = r.guide[2] = r.guide[3] = 0;
   }
   return rec;
 }

@@ -313,6 +313,13 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
   } else {
     a.site[i].total = acc;                  // scatterer.h:91  _max_rate = neighbors.back().first
     a.site[i].inv_total = d ? 1. / acc : 0.0;  // scatterer.h:92
+    uint8_t g8[kGuideBuckets];
+    build_guide(a.cum + base, d, acc, g8);  // reads back this thread's own row
+    uint32_t g[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < kGuideBuckets; ++j) g[j >> 2] |= (uint32_t)g8[j] << ((j & 3) * 8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.site[i].guide[j] = g[j];
     a.site[i].row_begin = (uint32_t)base;
     a.site[i].row_len = d;
     if (d == 0) atomicOr(a.flags + FLAG_EMPTY_ROW, 1);

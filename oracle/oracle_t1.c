@@ -25,9 +25,10 @@
  * normalise divides by the norm, or by 1 if the norm is not > 0.  glibc supplies rand()/log()/acos()/pow()/cos()/sin().
  *
  * Draw sources.  GLIBC: one global sequential stream, rand(), excitons visited in index order -- the reference's
- * OMP_NUM_THREADS=1 behaviour.  PHILOX: draw k of exciton g is word (k&3) of Philox4x32-10(ctr={k>>2 lo, k>>2 hi, g lo,
- * g hi}, key={seed lo, seed hi}) shifted right by one bit (31 bits, so RAND_MAX arithmetic is unchanged) -- the stream
- * the CUDA engine uses.  REPLAY: per-exciton lists of recorded draws.
+ * OMP_NUM_THREADS=1 behaviour.  PHILOX: draw k of exciton g is word (k&1) of Philox2x32-10(ctr={k>>1, g lo}, key =
+ * seed lo ^ rot16(seed hi) ^ g hi * 0x9E3779B9) shifted right by one bit (31 bits, so RAND_MAX arithmetic is unchanged)
+ * -- the stream the CUDA engine uses: two words per call, which is what one scattering event consumes.
+ * REPLAY: per-exciton lists of recorded draws.
  *
  * Build: gcc -O2 -std=c99 -ffp-contract=off (no FMA contraction, like the reference's x86-64 baseline build).
  */
@@ -88,13 +89,27 @@ void t1_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* Philox2x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) */
+void t1_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1];
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p = (uint64_t)0xD256D193u * c0;
+    const uint32_t n0 = (uint32_t)(p >> 32) ^ key ^ c1;
+    c1 = (uint32_t)p;
+    c0 = n0;
+    key += 0x9E3779B9u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+}
+
 int32_t t1_philox_draw(uint64_t seed, uint64_t exciton, uint64_t k) {
-  const uint64_t blk = k >> 2;
-  const uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)exciton, (uint32_t)(exciton >> 32)};
-  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-  uint32_t       o[4];
-  t1_philox4x32_10(ctr, key, o);
-  return (int32_t)(o[k & 3] >> 1);
+  const uint32_t sh = (uint32_t)(seed >> 32), gh = (uint32_t)(exciton >> 32);
+  const uint32_t key = (uint32_t)seed ^ ((sh << 16) | (sh >> 16)) ^ (gh * 0x9E3779B9u);
+  const uint32_t ctr[2] = {(uint32_t)(k >> 1), (uint32_t)exciton};
+  uint32_t       o[2];
+  t1_philox2x32_10(ctr, key, o);
+  return (int32_t)(o[k & 1] >> 1);
 }
 
 /* monte_carlo.cpp:172-193.  normalise(r1) is the zero vector when ash1 == 0 (divide by 1). */

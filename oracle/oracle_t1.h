@@ -21,6 +21,7 @@ enum { T1_DRAWS_GLIBC = 0, T1_DRAWS_PHILOX = 1, T1_DRAWS_REPLAY = 2 };
 /* ---- stand-alone pieces (known-answer testable) ------------------------------------------------------------ */
 void   t1_linspace(double start, double end, int64_t n, double* out);
 void   t1_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void   t1_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]);
 int32_t t1_philox_draw(uint64_t seed, uint64_t exciton, uint64_t k); /* 31-bit draw k of an exciton's stream */
 void   t1_forster_table(double gamma0, const int32_t dims[4], const double* theta, const double* z, const double* a1,
                         const double* a2, double* rates);

@@ -37,6 +37,7 @@ def _lib():
     sig = {
         "t1_linspace": (None, [D, D, I64, V]),
         "t1_philox4x32_10": (None, [V, V, V]),
+        "t1_philox2x32_10": (None, [V, C.c_uint32, V]),
         "t1_philox_draw": (I32, [U64, U64, U64]),
         "t1_forster_table": (None, [D, V, V, V, V, V, V]),
         "t1_select": (I64, [V, I64, D]),
@@ -113,6 +114,12 @@ def linspace(a: float, b: float, n: int) -> np.ndarray:
 def philox4x32_10(ctr, key) -> np.ndarray:
     c, k, o = np.asarray(ctr, np.uint32), np.asarray(key, np.uint32), np.empty(4, np.uint32)
     lib().t1_philox4x32_10(_p(c), _p(k), _p(o))
+    return o
+
+
+def philox2x32_10(ctr, key: int) -> np.ndarray:
+    c, o = np.asarray(ctr, np.uint32), np.empty(2, np.uint32)
+    lib().t1_philox2x32_10(_p(c), key, _p(o))
     return o
 
 

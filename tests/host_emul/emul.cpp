@@ -108,6 +108,11 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
       e->row_ptr[i + 1] = e->row_ptr[i] + d;
       e->site[i].total = acc;
       e->site[i].inv_total = d ? 1. / acc : 0.0;
+      {
+        uint8_t g[kGuideBuckets];
+        build_guide(e->cum.data() + e->row_ptr[i], d, acc, g);
+        memcpy(e->site[i].guide, g, sizeof(g));
+      }
       e->site[i].row_begin = (uint32_t)e->row_ptr[i];
       e->site[i].row_len = d;
       e->guards += guard;
@@ -256,7 +261,24 @@ void emul_trace(Emul* e, int32_t* flat) {
   for (auto& v : e->trace)
     for (int32_t s : v) flat[k++] = s;
 }
-int64_t emul_select(const double* cum, int64_t d, double dice) { return (int64_t)select_entry(cum, (uint32_t)d, dice); }
+int64_t emul_select(const double* cum, int64_t d, double dice) { return (int64_t)select_entry(cum, 0u, (uint32_t)d - 1u, dice); }
+// guided search exactly as after_flight_scatter performs it for draw r
+int64_t emul_select_guided(const double* cum, int64_t d, int32_t r) {
+  const double total = cum[d - 1];
+  uint8_t      g8[kGuideBuckets];
+  build_guide(cum, (uint32_t)d, total, g8);
+  uint32_t g[4];
+  memcpy(g, g8, sizeof(g));
+  const double dice = total * (double)r / kRandMax;
+  uint32_t     lo = 0, hi = (uint32_t)d - 1;
+  if ((uint32_t)d <= kGuideMaxRow) {
+    const uint32_t j = (uint32_t)r >> kGuideShift;
+    lo = guide_byte(g, j);
+    if (j + 1 < (uint32_t)kGuideBuckets) hi = guide_byte(g, j + 1);
+  }
+  return (int64_t)select_entry(cum, lo, hi, dice);
+}
+void emul_philox2x32(uint32_t c0, uint32_t c1, uint32_t k, uint32_t* out) { philox2x32_10(c0, c1, k, out); }
 }  // extern "C"
 
 // ---- scheduling study support: the per-exciton sequence of micro-operations of one launch ----------------------------

@@ -88,6 +88,32 @@ def test_select_entry_equals_reference_loop():
             assert e.select(c, dice) == T1m.select(c, dice)
 
 
+def test_guided_search_equals_reference_loop_for_every_bucket():
+    e = Emul(base_mc())
+    rng = np.random.default_rng(5)
+    e.L.emul_select_guided.restype = __import__("ctypes").c_int64
+    e.L.emul_select_guided.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int64, __import__("ctypes").c_int32]
+    for _ in range(1500):
+        d = int(rng.integers(1, 300))  # rows above 255 entries bypass the guide
+        c = np.ascontiguousarray(np.cumsum(rng.random(d) ** 8 * (rng.random(d) > 0.2) * 10.0 ** rng.integers(8, 15)))
+        if c[-1] == 0:
+            continue
+        draws = np.concatenate([rng.integers(0, 2 ** 31, 24), np.arange(16) << 27, (np.arange(1, 17) << 27) - 1, [0, 2 ** 31 - 1]])
+        for r in draws:
+            r = int(min(r, 2 ** 31 - 1))
+            dice = c[-1] * float(r) / 2147483647.0
+            assert e.L.emul_select_guided(c.ctypes.data, d, r) == T1m.select(c, dice)
+
+
+def test_engine_core_uses_the_same_philox_stream_as_the_oracle():
+    import ctypes
+    e = Emul(base_mc())
+    out = (ctypes.c_uint32 * 2)()
+    e.L.emul_philox2x32.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
+    e.L.emul_philox2x32(0x243F6A88, 0x85A308D3, 0x13198A2E, out)
+    assert [hex(x) for x in out] == ["0xdd7ce038", "0xf62a4c12"]
+
+
 def test_untrimmed_bigger_film_against_oracle():
     pos, ori = film.film(NT=120, NP=60, a=5.0, LX=300.0, LY=80.0, seed=5)
     mc = base_mc()

@@ -16,12 +16,22 @@ def test_philox_known_answers():
         "0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
 
 
+def test_philox2x32_known_answers():
+    # Random123 kat_vectors for philox2x32-10: the generator behind the engine's exciton streams
+    assert [hex(x) for x in T1m.philox2x32_10([0, 0], 0)] == ["0xff1dae59", "0x6cd10df2"]
+    assert [hex(x) for x in T1m.philox2x32_10([0xFFFFFFFF, 0xFFFFFFFF], 0xFFFFFFFF)] == ["0x2c3f628b", "0xab4fd7ad"]
+    assert [hex(x) for x in T1m.philox2x32_10([0x243F6A88, 0x85A308D3], 0x13198A2E)] == ["0xdd7ce038", "0xf62a4c12"]
+
+
 def test_philox_draw_layout():
-    # draw k of exciton g = word k&3 of block k>>2, shifted to 31 bits
-    seed, g = 0x1234567890ABCDEF, 0x0000000500000007
-    for k in (0, 1, 2, 3, 4, 9, 1023):
-        blk = T1m.philox4x32_10([k >> 2, 0, g & 0xFFFFFFFF, g >> 32], [seed & 0xFFFFFFFF, seed >> 32])
-        assert T1m.philox_draw(seed, g, k) == int(blk[k & 3]) >> 1
+    # draw k of exciton g = word k&1 of block k>>1 of the stream keyed by (seed, g), shifted to 31 bits
+    for seed, g in ((7, 12345), (0x1234567890ABCDEF, 0x0000000500000007)):
+        sh, gh = seed >> 32, g >> 32
+        key = (seed & 0xFFFFFFFF) ^ (((sh << 16) | (sh >> 16)) & 0xFFFFFFFF) ^ ((gh * 0x9E3779B9) & 0xFFFFFFFF)
+        for k in (0, 1, 2, 3, 4, 9, 1023):
+            blk = T1m.philox2x32_10([k >> 1, g & 0xFFFFFFFF], key)
+            assert T1m.philox_draw(seed, g, k) == int(blk[k & 1]) >> 1
+    assert T1m.philox_draw(7, 12345, 0) == int(T1m.philox2x32_10([0, 12345], 7)[0]) >> 1  # small seeds: key == seed
 
 
 def test_glibc_srand100_first_draws():
