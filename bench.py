@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--intervals", type=int, default=100, help="sampling intervals (dt = 1e-13 s) per bench step")
     ap.add_argument("--chunk", type=int, default=64)
     ap.add_argument("--sort", type=int, default=1)
-    ap.add_argument("--occupancy", type=int, default=6, help="resident 128-thread blocks per SM of the hop kernel (4, 5, 6, 8)")
+    ap.add_argument("--occupancy", type=int, default=5, help="resident 128-thread blocks per SM of the hop kernel (4, 5, 6, 8)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-excitons", type=int, default=8000)
     ap.add_argument("--cpu-intervals", type=int, default=400)

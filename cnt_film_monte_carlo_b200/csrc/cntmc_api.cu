@@ -140,7 +140,7 @@ struct cntmc_handle {
   int64_t opt_chunk = 64;   // time steps per launch
   int64_t opt_sort = 1;     // regroup excitons by activity between launches
   int64_t opt_block = 128;  // threads per block of the hop kernel
-  int64_t opt_occupancy = 6;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
+  int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
   int64_t opt_stage_mb = 4096;  // cap on the (step, exciton) staging buffer; shortens the launches if needed
   int     sm_count = 0;
   int64_t opt_time_kernels = 0;  // CUDA events around every hop-kernel launch (bench.py's roofline figure)
@@ -381,9 +381,9 @@ template <typename Draws>
 void launch_kubo(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) {
   switch (h->opt_occupancy) {
     case 4: kubo_kernel<Draws, 4><<<grid, 128, 0, st>>>(a); break;
-    case 5: kubo_kernel<Draws, 5><<<grid, 128, 0, st>>>(a); break;
     case 8: kubo_kernel<Draws, 8><<<grid, 128, 0, st>>>(a); break;
-    default: kubo_kernel<Draws, 6><<<grid, 128, 0, st>>>(a); break;
+    case 6: kubo_kernel<Draws, 6><<<grid, 128, 0, st>>>(a); break;
+    default: kubo_kernel<Draws, 5><<<grid, 128, 0, st>>>(a); break;
   }
 }
 

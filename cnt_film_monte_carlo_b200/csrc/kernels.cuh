@@ -38,32 +38,32 @@ struct DrawConfig {
 };
 
 __device__ __forceinline__ void load_lane(Lane& L, const ExcitonArrays& S, const Tables& T, int64_t e) {
-  L.px = S.px[e];
-  L.py = S.py[e];
-  L.pz = S.pz[e];
-  L.dx = S.dx[e];
-  L.dy = S.dy[e];
-  L.dz = S.dz[e];
-  L.ff = S.ff[e];
-  L.site = S.site[e];
-  L.heading_right = S.heading[e] != 0;
-  L.ndraw = S.ndraw[e];
+  L.px = __ldcs(S.px + e);  // exciton state streams through once per launch
+  L.py = __ldcs(S.py + e);
+  L.pz = __ldcs(S.pz + e);
+  L.dx = __ldcs(S.dx + e);
+  L.dy = __ldcs(S.dy + e);
+  L.dz = __ldcs(S.dz + e);
+  L.ff = __ldcs(S.ff + e);
+  L.site = __ldcs(S.site + e);
+  L.heading_right = __ldcs(S.heading + e) != 0;
+  L.ndraw = __ldcs(S.ndraw + e);
   L.nevent = 0;
   L.stuck = false;
   attach_site(L, T);
 }
 __device__ __forceinline__ void store_lane(const Lane& L, const ExcitonArrays& S, int64_t e) {  // needs L.pos_valid
-  S.px[e] = L.px;
-  S.py[e] = L.py;
-  S.pz[e] = L.pz;
-  S.dx[e] = L.dx;
-  S.dy[e] = L.dy;
-  S.dz[e] = L.dz;
-  S.ff[e] = L.ff;
-  S.site[e] = L.site;
-  S.heading[e] = L.heading_right ? 1 : 0;
-  S.ndraw[e] = L.ndraw;
-  S.last_events[e] = L.nevent;
+  __stcs(S.px + e, L.px);
+  __stcs(S.py + e, L.py);
+  __stcs(S.pz + e, L.pz);
+  __stcs(S.dx + e, L.dx);
+  __stcs(S.dy + e, L.dy);
+  __stcs(S.dz + e, L.dz);
+  __stcs(S.ff + e, L.ff);
+  __stcs(S.site + e, L.site);
+  __stcs(S.heading + e, (uint8_t)(L.heading_right ? 1 : 0));
+  __stcs(S.ndraw + e, L.ndraw);
+  __stcs(S.last_events + e, L.nevent);
 }
 
 template <typename Draws>
@@ -171,10 +171,11 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
     if (have) {
       if (advance(L, a.T, D, c, trace, (uint32_t)(a.trace_cap - trace_base))) {
         const size_t slot = (size_t)c.step * (size_t)a.P + (size_t)q;
-        a.stage[slot] = L.dx * L.dx;  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
-        a.stage[plane + slot] = L.dy * L.dy;
-        a.stage[2 * plane + slot] = L.dz * L.dz;
-        a.stage_ev[slot] = L.nevent - c.ev0;
+        // streaming stores: written once, read once by the reduction, must not evict the tables from L2
+        __stcs(a.stage + slot, L.dx * L.dx);  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
+        __stcs(a.stage + plane + slot, L.dy * L.dy);
+        __stcs(a.stage + 2 * plane + slot, L.dz * L.dz);
+        __stcs(a.stage_ev + slot, L.nevent - c.ev0);
         ++c.step;
         begin_step(c, L, a.dt);
       }
@@ -224,10 +225,10 @@ __global__ void __launch_bounds__(256) reduce_stage_kernel(const double* stage, 
   const size_t      row = (size_t)s * (size_t)P;
   double            v[4] = {0, 0, 0, 0};
   for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-    v[0] += stage[row + q];
-    v[1] += stage[plane + row + q];
-    v[2] += stage[2 * plane + row + q];
-    v[3] += (double)stage_ev[row + q];
+    v[0] += __ldcs(stage + row + q);
+    v[1] += __ldcs(stage + plane + row + q);
+    v[2] += __ldcs(stage + 2 * plane + row + q);
+    v[3] += (double)__ldcs(stage_ev + row + q);
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) sh[threadIdx.x][c] = v[c];
