@@ -57,7 +57,6 @@ SIGNATURES = {
     "cntmc_csr_midpoint_guards": (I64, [V]),
     "cntmc_csr_build_seconds": (D, [V]),
     "cntmc_get_particles": (C.c_int, [V, V, V, V, V, V, V]),
-    "cntmc_get_old_pos": (C.c_int, [V, V]),
     "cntmc_trace_enable": (C.c_int, [V, I32]),
     "cntmc_trace_get": (C.c_int, [V, V, V]),
     "cntmc_set_option": (C.c_int, [V, CP, I64]),

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -49,6 +50,10 @@ struct DevBuf {
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
+  void swap(DevBuf& o) {
+    std::swap(p, o.p);
+    std::swap(n, o.n);
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -73,6 +78,40 @@ struct DevBuf {
 thread_local std::string g_create_error;
 
 }  // namespace
+
+// one copy of the exciton population on the device (contact mode keeps two and compacts from one into the other)
+struct ExcitonStore {
+  DevBuf<double>   px, py, pz, dx, dy, dz, ff;
+  DevBuf<int32_t>  site;
+  DevBuf<uint8_t>  heading;
+  DevBuf<uint32_t> ndraw, events;
+  DevBuf<uint64_t> gid;
+  void alloc(size_t n, bool with_gid) {
+    px.alloc(n); py.alloc(n); pz.alloc(n);
+    dx.alloc(n); dy.alloc(n); dz.alloc(n);
+    ff.alloc(n);
+    site.alloc(n); heading.alloc(n); ndraw.alloc(n); events.alloc(n);
+    if (with_gid) gid.alloc(n);
+  }
+  void swap(ExcitonStore& o) {
+    px.swap(o.px); py.swap(o.py); pz.swap(o.pz);
+    dx.swap(o.dx); dy.swap(o.dy); dz.swap(o.dz);
+    ff.swap(o.ff);
+    site.swap(o.site); heading.swap(o.heading); ndraw.swap(o.ndraw); events.swap(o.events); gid.swap(o.gid);
+  }
+  ExcitonArrays view(bool with_gid) const {
+    ExcitonArrays S{};
+    S.px = px.p; S.py = py.p; S.pz = pz.p;
+    S.dx = dx.p; S.dy = dy.p; S.dz = dz.p;
+    S.ff = ff.p;
+    S.site = site.p;
+    S.heading = heading.p;
+    S.ndraw = ndraw.p;
+    S.last_events = events.p;
+    S.gid = with_gid ? gid.p : nullptr;
+    return S;
+  }
+};
 
 struct cntmc_handle {
   mutable std::string err;
@@ -111,11 +150,10 @@ struct cntmc_handle {
 
   // excitons
   int64_t          P = 0, capacity = 0;
-  DevBuf<double>   e_px, e_py, e_pz, e_dx, e_dy, e_dz, e_ff, e_ox, e_oy, e_oz;
-  DevBuf<int32_t>  e_site;
-  DevBuf<uint8_t>  e_heading;
-  DevBuf<uint32_t> e_ndraw, e_events, e_keys_out, e_iota, e_perm;
-  DevBuf<uint64_t> e_gid;
+  ExcitonStore     ex, ex_spare;
+  DevBuf<uint32_t> e_keys_out, e_iota, e_perm;
+  DevBuf<uint8_t>  d_alive;
+  uint64_t         next_gid = 0;
   DevBuf<char>     sort_tmp;
   bool             have_events = false;
   DrawConfig       draws{};
@@ -156,32 +194,43 @@ struct cntmc_handle {
     if (ev1) cudaEventDestroy(ev1);
   }
 
-  ExcitonArrays arrays() {
-    ExcitonArrays S{};
-    S.px = e_px.p; S.py = e_py.p; S.pz = e_pz.p;
-    S.dx = e_dx.p; S.dy = e_dy.p; S.dz = e_dz.p;
-    S.ff = e_ff.p;
-    S.site = e_site.p;
-    S.heading = e_heading.p;
-    S.ndraw = e_ndraw.p;
-    S.last_events = e_events.p;
-    S.gid = contact_mode ? e_gid.p : nullptr;
-    return S;
-  }
-  void alloc_excitons(int64_t cap) {
-    const size_t n = (size_t)cap;
-    e_px.alloc(n); e_py.alloc(n); e_pz.alloc(n);
-    e_dx.alloc(n); e_dy.alloc(n); e_dz.alloc(n);
-    e_ff.alloc(n);
-    e_site.alloc(n); e_heading.alloc(n); e_ndraw.alloc(n); e_events.alloc(n);
-    e_keys_out.alloc(n); e_iota.alloc(n); e_perm.alloc(n);
-    if (contact_mode) {
-      e_ox.alloc(n); e_oy.alloc(n); e_oz.alloc(n);
-      e_gid.alloc(n);
-    }
+  ExcitonArrays arrays() { return ex.view(contact_mode); }
+  // contact mode: room for `cap` work items in both copies, keeping the first `keep` excitons of the live copy
+  void reserve_contact(int64_t cap, int64_t keep);
+  void          alloc_excitons(int64_t cap) {
+    ex.alloc((size_t)cap, contact_mode);
+    e_keys_out.alloc((size_t)cap);
+    e_iota.alloc((size_t)cap);
+    e_perm.alloc((size_t)cap);
     capacity = cap;
   }
 };
+
+template <typename T>
+static void grow_keep(DevBuf<T>& b, size_t cap, size_t keep, cudaStream_t st) {
+  if (cap <= b.n && b.p) return;
+  DevBuf<T> nb;
+  nb.alloc(cap);
+  if (keep && b.p) CUDA_CHECK(cudaMemcpyAsync(nb.p, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  std::swap(b.p, nb.p);
+  std::swap(b.n, nb.n);
+}
+void cntmc_handle::reserve_contact(int64_t cap, int64_t keep) {
+  if (cap <= capacity) return;
+  const size_t c = (size_t)(cap + cap / 4 + 1024), k = (size_t)keep;
+  grow_keep(ex.px, c, k, stream); grow_keep(ex.py, c, k, stream); grow_keep(ex.pz, c, k, stream);
+  grow_keep(ex.dx, c, k, stream); grow_keep(ex.dy, c, k, stream); grow_keep(ex.dz, c, k, stream);
+  grow_keep(ex.ff, c, k, stream);
+  grow_keep(ex.site, c, k, stream); grow_keep(ex.heading, c, k, stream); grow_keep(ex.ndraw, c, k, stream);
+  grow_keep(ex.events, c, k, stream); grow_keep(ex.gid, c, k, stream);
+  ex_spare.alloc(c, true);
+  d_alive.alloc(c);
+  e_iota.alloc(c);
+  e_perm.alloc(c);
+  e_keys_out.alloc(c);
+  capacity = (int64_t)c;
+}
 
 namespace {
 
@@ -367,7 +416,7 @@ void create_common(cntmc_t* h, int64_t P) {
   h->hops = h->reinjections = 0;
   h->crossings = h->probes = 0;
   CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, CTR_COUNT * sizeof(unsigned long long), h->stream));
-  CUDA_CHECK(cudaMemsetAsync(h->e_events.p, 0, (size_t)P * sizeof(uint32_t), h->stream));
+  CUDA_CHECK(cudaMemsetAsync(h->ex.events.p, 0, (size_t)P * sizeof(uint32_t), h->stream));
   if (h->replay)
     launch_create<ReplayDraws>(h, P, h->d_inject.p, (int32_t)h->inj.sites.size());
   else
@@ -417,10 +466,10 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
       // queue order: most active excitons (events in the previous launch) first
       iota_kernel<<<(unsigned)((h->P + 255) / 256), 256, 0, st>>>(h->e_iota.p, h->P);
       size_t bytes = 0;
-      cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->e_events.p, h->e_keys_out.p, h->e_iota.p, h->e_perm.p,
+      cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->ex.events.p, h->e_keys_out.p, h->e_iota.p, h->e_perm.p,
                                                 (int)h->P, 0, 32, st);
       h->sort_tmp.alloc(bytes);
-      CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp.p, bytes, h->e_events.p, h->e_keys_out.p, h->e_iota.p,
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp.p, bytes, h->ex.events.p, h->e_keys_out.p, h->e_iota.p,
                                                            h->e_perm.p, (int)h->P, 0, 32, st));
       order = h->e_perm.p;
       h->last_launches += 1;
@@ -683,20 +732,20 @@ int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P,
     if (P != h->P) h->have_events = false;
     h->P = P;
     const size_t n = (size_t)P;
-    h->e_site.upload(site, n, st);
-    h->e_px.upload(pos, n, st); h->e_py.upload(pos + n, n, st); h->e_pz.upload(pos + 2 * n, n, st);
-    h->e_dx.upload(delta, n, st); h->e_dy.upload(delta + n, n, st); h->e_dz.upload(delta + 2 * n, n, st);
-    h->e_ff.upload(ff, n, st);
-    h->e_heading.upload(heading, n, st);
-    h->e_ndraw.upload(ndraw, n, st);
+    h->ex.site.upload(site, n, st);
+    h->ex.px.upload(pos, n, st); h->ex.py.upload(pos + n, n, st); h->ex.pz.upload(pos + 2 * n, n, st);
+    h->ex.dx.upload(delta, n, st); h->ex.dy.upload(delta + n, n, st); h->ex.dz.upload(delta + 2 * n, n, st);
+    h->ex.ff.upload(ff, n, st);
+    h->ex.heading.upload(heading, n, st);
+    h->ex.ndraw.upload(ndraw, n, st);
     h->d_sums.alloc((size_t)nsteps * 4);
     kubo_step_device(h, dt, nsteps, h->d_sums.p);
-    h->e_site.download(site, n, st);
-    h->e_px.download(pos, n, st); h->e_py.download(pos + n, n, st); h->e_pz.download(pos + 2 * n, n, st);
-    h->e_dx.download(delta, n, st); h->e_dy.download(delta + n, n, st); h->e_dz.download(delta + 2 * n, n, st);
-    h->e_ff.download(ff, n, st);
-    h->e_heading.download(heading, n, st);
-    h->e_ndraw.download(ndraw, n, st);
+    h->ex.site.download(site, n, st);
+    h->ex.px.download(pos, n, st); h->ex.py.download(pos + n, n, st); h->ex.pz.download(pos + 2 * n, n, st);
+    h->ex.dx.download(delta, n, st); h->ex.dy.download(delta + n, n, st); h->ex.dz.download(delta + 2 * n, n, st);
+    h->ex.ff.download(ff, n, st);
+    h->ex.heading.download(heading, n, st);
+    h->ex.ndraw.download(ndraw, n, st);
     finish_step_host(h, nsteps, msd_out);
   });
 }
@@ -710,24 +759,211 @@ int64_t cntmc_reinjections(const cntmc_t* h) { return h->reinjections; }
 int64_t cntmc_crossings(const cntmc_t* h) { return h->crossings; }
 int64_t cntmc_probes(const cntmc_t* h) { return h->probes; }
 
-// ---- contact flavour: see contacts.cuh (added once the Green-Kubo path is parity-green) ------------------------------
-int cntmc_init(cntmc_t* h, int64_t, int64_t, uint64_t, int64_t) {
-  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+// ---- contact flavour ----------------------------------------------------------------------------------------------------
+int cntmc_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_t capacity) {
+  return guarded(h, [&] {
+    require(h->prm.n_seg >= 2, "\"number of segments\" must be at least 2 in contact mode");
+    require(c1_pop >= 0 && c2_pop >= 0, "contact populations must be non-negative");
+    h->contact_mode = true;
+    common_init(h);
+    const int n_seg = h->n_seg = h->prm.n_seg;
+    cudaStream_t st = h->stream;
+    h->area = slab_areas(h->sites, h->dom, n_seg);                      // monte_carlo.h:184
+    h->c1_sites = contact_sites(h->sites, h->dom, n_seg, 1);            // monte_carlo.h:188
+    h->c2_sites = contact_sites(h->sites, h->dom, n_seg, n_seg);        // monte_carlo.h:189
+    if ((c1_pop > 0 && h->c1_sites.empty()) || (c2_pop > 0 && h->c2_sites.empty()))
+      throw StateError("a contact with a non-zero population holds no site (rand() % 0 in the reference, monte_carlo.h:477)");
+    h->d_c1.upload(h->c1_sites, st);
+    h->d_c2.upload(h->c2_sites, st);
+    h->c1_pop = c1_pop;
+    h->c2_pop = c2_pop;
+    h->replay = false;
+    h->draws = DrawConfig{};
+    h->draws.seed = seed;
+    h->draws.first_gid = 0;
+    // create_particles (monte_carlo.h:274-316): linear profile over the slabs, sites from the half-open slab lists
+    const double         dp = double(c2_pop - c1_pop) / (double(n_seg) - 1);
+    std::vector<int64_t> count_off((size_t)n_seg + 1, 0), site_off((size_t)n_seg + 1, 0);
+    std::vector<int32_t> slab_sites;
+    for (int i = 0; i < n_seg; ++i) {
+      const int64_t n_particle = (int64_t)std::round(double(c1_pop) + double(i) * dp);
+      const auto    list = slab_sites_half_open(h->sites, h->dom, n_seg, i);
+      if (n_particle > 0 && list.empty())
+        throw StateError("a slab that must receive excitons holds no site (rand() % 0 in the reference, monte_carlo.h:305)");
+      slab_sites.insert(slab_sites.end(), list.begin(), list.end());
+      site_off[(size_t)i + 1] = (int64_t)slab_sites.size();
+      count_off[(size_t)i + 1] = count_off[(size_t)i] + std::max<int64_t>(n_particle, 0);
+    }
+    const int64_t P0 = count_off[(size_t)n_seg];
+    h->capacity = 0;
+    h->reserve_contact(std::max<int64_t>(capacity, P0 + 1), 0);
+    h->P = P0;
+    h->next_gid = (uint64_t)P0;
+    h->time = 0;
+    h->hops = h->reinjections = h->crossings = h->probes = 0;
+    if (P0 > 0) {
+      DevBuf<int64_t> d_count_off, d_site_off;
+      DevBuf<int32_t> d_slab_sites;
+      d_count_off.upload(count_off, st);
+      d_site_off.upload(site_off, st);
+      d_slab_sites.upload(slab_sites, st);
+      ContactCreateArgs a{};
+      a.T = h->T;
+      a.S = h->arrays();
+      a.draws = h->draws;
+      a.P = P0;
+      a.count_off = d_count_off.p;
+      a.site_off = d_site_off.p;
+      a.slab_sites = d_slab_sites.p;
+      a.n_seg = n_seg;
+      a.alive = h->d_alive.p;
+      a.flags = h->d_flags.p;
+      create_contact_population_kernel<PhiloxDraws><<<(unsigned)((P0 + 255) / 256), 256, 0, st>>>(a);
+      CUDA_CHECK(cudaGetLastError());
+      check_flags(h);  // synchronises before the temporaries go away
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    h->initialised = true;
+  });
 }
-int cntmc_step(cntmc_t* h, double, int64_t, int64_t*, int64_t*) {
-  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+
+// nsteps iterations of { step ; metrics ; repopulate_contacts } -> dev_bins[nsteps][2*n_seg-1] (device, 64-bit counts)
+static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned long long* dev_bins) {
+  require(h->initialised && h->contact_mode, "call cntmc_init first");
+  require(nsteps > 0, "nsteps must be positive");
+  use_device(h);
+  cudaStream_t st = h->stream;
+  if (h->sm_count == 0) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int     nb = 2 * h->n_seg - 1;
+  const int64_t C = h->c1_pop + h->c2_pop;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({h->opt_chunk, nsteps, (int64_t)(40000 / (nb * 4))}));
+  DevBuf<unsigned long long> d_count;
+  d_count.alloc(1);
+  h->last_launches = 0;
+  CUDA_CHECK(cudaEventRecord(h->ev0, st));
+  CUDA_CHECK(cudaMemsetAsync(dev_bins, 0, (size_t)nsteps * nb * sizeof(unsigned long long), st));
+  for (int64_t done = 0; done < nsteps; done += chunk) {
+    const int     n = (int)std::min(chunk, nsteps - done);
+    const int64_t W = h->P + (int64_t)n * C;
+    if (W == 0) {
+      for (int s = 0; s < n; ++s) h->time += dt;
+      continue;
+    }
+    h->reserve_contact(W, h->P);
+    const unsigned grid = (unsigned)std::min<int64_t>((W + 127) / 128, (int64_t)h->sm_count * h->opt_occupancy);
+    set_u64_kernel<<<1, 1, 0, st>>>(h->d_counters.p + CTR_QUEUE, (unsigned long long)grid * 128ull);
+    ContactArgs a{};
+    a.T = h->T;
+    a.S = h->arrays();
+    a.draws = h->draws;
+    a.alive = h->d_alive.p;
+    a.P_alive = h->P;
+    a.c1_pop = h->c1_pop;
+    a.c2_pop = h->c2_pop;
+    a.c1_sites = h->d_c1.p;
+    a.c2_sites = h->d_c2.p;
+    a.n_c1 = (int32_t)h->c1_sites.size();
+    a.n_c2 = (int32_t)h->c2_sites.size();
+    a.next_gid = h->next_gid;
+    a.dt = dt;
+    a.nsteps = n;
+    a.n_seg = h->n_seg;
+    a.ymin = h->dom.lo[1];
+    a.ymax = h->dom.hi[1];
+    a.dy = (h->dom.hi[1] - h->dom.lo[1]) / double(h->n_seg);  // monte_carlo.h:446
+    a.bins = dev_bins + done * nb;
+    a.flags = h->d_flags.p;
+    a.counters = h->d_counters.p;
+    const size_t smem = (size_t)n * nb * sizeof(int);
+    switch (h->opt_occupancy) {
+      case 4: contact_kernel<PhiloxDraws, 4><<<grid, 128, smem, st>>>(a); break;
+      case 6: contact_kernel<PhiloxDraws, 6><<<grid, 128, smem, st>>>(a); break;
+      case 8: contact_kernel<PhiloxDraws, 8><<<grid, 128, smem, st>>>(a); break;
+      default: contact_kernel<PhiloxDraws, 5><<<grid, 128, smem, st>>>(a); break;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    // survivors, in work-item order, move to the front of the spare copy
+    iota_kernel<<<(unsigned)((W + 255) / 256), 256, 0, st>>>(h->e_iota.p, W);
+    size_t bytes = 0;
+    cub::DeviceSelect::Flagged(nullptr, bytes, h->e_iota.p, h->d_alive.p, h->e_perm.p, d_count.p, (int)W, st);
+    h->sort_tmp.alloc(bytes);
+    CUDA_CHECK(cub::DeviceSelect::Flagged(h->sort_tmp.p, bytes, h->e_iota.p, h->d_alive.p, h->e_perm.p, d_count.p, (int)W, st));
+    unsigned long long survivors = 0;
+    d_count.download(&survivors, 1, st);
+    check_flags(h);  // synchronises
+    if (survivors > 0) {
+      gather_excitons_kernel<<<(unsigned)((survivors + 255) / 256), 256, 0, st>>>(h->ex.view(true), h->ex_spare.view(true), h->e_perm.p,
+                                                                                (int64_t)survivors);
+      CUDA_CHECK(cudaGetLastError());
+    }
+    h->ex.swap(h->ex_spare);
+    h->P = (int64_t)survivors;
+    h->next_gid += (uint64_t)((int64_t)n * C);
+    h->last_launches += 4;
+    for (int s = 0; s < n; ++s) h->time += dt;  // monte_carlo.h:354
+  }
+  CUDA_CHECK(cudaEventRecord(h->ev1, st));
 }
-int cntmc_step_dev(cntmc_t* h, double, int64_t, int64_t*) {
-  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+
+int cntmc_step_dev(cntmc_t* h, double dt, int64_t nsteps, int64_t* dev_bins) {
+  return guarded(h, [&] {
+    require(dev_bins != nullptr, "null device buffer");
+    contact_step_device(h, dt, nsteps, reinterpret_cast<unsigned long long*>(dev_bins));
+  });
 }
-int cntmc_get_area(const cntmc_t* h, double*) {
-  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+
+int cntmc_step(cntmc_t* h, double dt, int64_t nsteps, int64_t* pop_out, int64_t* curr_out) {
+  return guarded(h, [&] {
+    require(h->initialised && h->contact_mode, "call cntmc_init first");
+    use_device(h);
+    const int                  nb = 2 * h->n_seg - 1;
+    DevBuf<unsigned long long> d_bins;
+    d_bins.alloc((size_t)nsteps * nb);
+    contact_step_device(h, dt, nsteps, d_bins.p);
+    std::vector<unsigned long long> bins((size_t)nsteps * nb);
+    d_bins.download(bins.data(), bins.size(), h->stream);
+    unsigned long long ctrs[CTR_COUNT];
+    h->d_counters.download(ctrs, CTR_COUNT, h->stream);
+    check_flags(h);
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    h->hops = (int64_t)ctrs[CTR_EVENTS];
+    h->crossings = (int64_t)ctrs[CTR_CROSS];
+    h->probes = (int64_t)ctrs[CTR_PROBE];
+    for (int64_t s = 0; s < nsteps; ++s) {
+      for (int i = 0; i < h->n_seg; ++i)
+        if (pop_out) pop_out[s * h->n_seg + i] = (int64_t)bins[(size_t)s * nb + i];
+      for (int i = 0; i + 1 < h->n_seg; ++i)
+        if (curr_out) curr_out[s * (h->n_seg - 1) + i] = (int64_t)bins[(size_t)s * nb + h->n_seg + i];
+    }
+  });
 }
-int cntmc_num_contact_sites(const cntmc_t* h, int, int64_t*) {
-  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+
+int cntmc_get_area(const cntmc_t* h, double* area) {
+  return guarded(h, [&] {
+    require(h->initialised && h->contact_mode, "call cntmc_init first");
+    std::copy(h->area.begin(), h->area.end(), area);
+  });
 }
-int cntmc_get_contact_sites(const cntmc_t* h, int, int32_t*) {
-  return guarded(h, [&] { throw std::invalid_argument("contact mode is not part of this build yet"); });
+int cntmc_num_contact_sites(const cntmc_t* h, int which, int64_t* n) {
+  return guarded(h, [&] {
+    require(h->initialised && h->contact_mode, "call cntmc_init first");
+    require(which == 1 || which == 2, "contact must be 1 or 2");
+    *n = (int64_t)(which == 1 ? h->c1_sites.size() : h->c2_sites.size());
+  });
+}
+int cntmc_get_contact_sites(const cntmc_t* h, int which, int32_t* ids) {
+  return guarded(h, [&] {
+    require(h->initialised && h->contact_mode, "call cntmc_init first");
+    require(which == 1 || which == 2, "contact must be 1 or 2");
+    const auto& l = which == 1 ? h->c1_sites : h->c2_sites;
+    std::copy(l.begin(), l.end(), ids);
+  });
 }
 int cntmc_number_of_segments(const cntmc_t* h) { return h->prm.n_seg; }
 
@@ -814,33 +1050,21 @@ int cntmc_get_particles(const cntmc_t* h, int32_t* site, double* pos, double* de
     use_device(h);
     const size_t n = (size_t)h->P;
     cudaStream_t st = h->stream;
-    if (site) h->e_site.download(site, n, st);
+    if (site) h->ex.site.download(site, n, st);
     if (pos) {
-      h->e_px.download(pos, n, st);
-      h->e_py.download(pos + n, n, st);
-      h->e_pz.download(pos + 2 * n, n, st);
+      h->ex.px.download(pos, n, st);
+      h->ex.py.download(pos + n, n, st);
+      h->ex.pz.download(pos + 2 * n, n, st);
     }
     if (delta) {
-      h->e_dx.download(delta, n, st);
-      h->e_dy.download(delta + n, n, st);
-      h->e_dz.download(delta + 2 * n, n, st);
+      h->ex.dx.download(delta, n, st);
+      h->ex.dy.download(delta + n, n, st);
+      h->ex.dz.download(delta + 2 * n, n, st);
     }
-    if (ff) h->e_ff.download(ff, n, st);
-    if (heading) h->e_heading.download(heading, n, st);
-    if (ndraw) h->e_ndraw.download(ndraw, n, st);
+    if (ff) h->ex.ff.download(ff, n, st);
+    if (heading) h->ex.heading.download(heading, n, st);
+    if (ndraw) h->ex.ndraw.download(ndraw, n, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
-  });
-}
-
-int cntmc_get_old_pos(const cntmc_t* h, double* old_pos) {
-  return guarded(h, [&] {
-    require(h->contact_mode && h->P > 0, "old positions are kept in contact mode only");
-    use_device(h);
-    const size_t n = (size_t)h->P;
-    h->e_ox.download(old_pos, n, h->stream);
-    h->e_oy.download(old_pos + n, n, h->stream);
-    h->e_oz.download(old_pos + 2 * n, n, h->stream);
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
   });
 }
 

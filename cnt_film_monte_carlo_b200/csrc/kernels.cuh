@@ -79,7 +79,7 @@ __device__ __forceinline__ void init_draws<ReplayDraws>(ReplayDraws& D, const Dr
 }
 
 enum { FLAG_STUCK = 0, FLAG_REPLAY = 1, FLAG_EMPTY_ROW = 2, FLAG_COUNT = 4 };
-enum { CTR_REINJECT = 0, CTR_GUARD = 1, CTR_CROSS = 2, CTR_PROBE = 3, CTR_QUEUE = 4, CTR_COUNT = 8 };
+enum { CTR_REINJECT = 0, CTR_GUARD = 1, CTR_CROSS = 2, CTR_PROBE = 3, CTR_QUEUE = 4, CTR_EVENTS = 5, CTR_COUNT = 8 };
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -254,6 +254,174 @@ __global__ void finish_sums_kernel(const double* partial, int nsteps, double* su
 __global__ void iota_kernel(uint32_t* v, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = (uint32_t)i;
+}
+
+// ---- K3: the hop kernel, contact flavour ---------------------------------------------------------------------------------
+// monte_carlo::step + save_population_profile + save_currents + repopulate_contacts (monte_carlo.h:343-355, 525-643,
+// 443-491) for nsteps iterations of the loop at main.cpp:98-106.
+//
+// Excitons never interact, and the contact rules are per-exciton: after the metrics of a step, an exciton whose y lies in
+// one of the two contact slabs is deleted, and exactly c1_pop + c2_pop fresh excitons are created on random contact
+// sites.  So a launch covers many steps: work item q < P_alive is an exciton alive at the start of the launch, work
+// item P_alive + s*C + j is the j-th exciton created after step s (stream id next_gid + s*C + j, first moved in step
+// s+1).  Every work item runs until it is deleted or the launch ends; population / current counts are integers and are
+// accumulated with integer atomics (shared memory per block, then global), so the result is order-independent.
+struct ContactArgs {
+  Tables              T;
+  ExcitonArrays       S;      // capacity >= P_alive + nsteps * (c1_pop + c2_pop); S.gid is required
+  DrawConfig          draws;
+  uint8_t*            alive;  // [work items]
+  int64_t             P_alive;
+  int64_t             c1_pop, c2_pop;
+  const int32_t *     c1_sites, *c2_sites;
+  int32_t             n_c1, n_c2;
+  uint64_t            next_gid;
+  double              dt;
+  int32_t             nsteps;
+  int32_t             n_seg;
+  double              ymin, ymax, dy;
+  unsigned long long* bins;  // [nsteps][2*n_seg-1]: population per slab, then net crossings per interface
+  int32_t*            flags;
+  unsigned long long* counters;
+};
+
+template <typename Draws, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) contact_kernel(const ContactArgs a) {
+  extern __shared__ int hist[];  // [nsteps][2*n_seg-1]
+  const int nb = 2 * a.n_seg - 1;
+  for (int k = threadIdx.x; k < a.nsteps * nb; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  const int      lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int64_t  C = a.c1_pop + a.c2_pop;
+  const int64_t  W = a.P_alive + (int64_t)a.nsteps * C;
+  const double   c1_hi = a.ymin + a.dy, c2_lo = a.ymin + double(a.n_seg - 1) * a.dy;  // monte_carlo.h:448-453
+  int64_t        q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool           have = q < W;
+  Lane           L{};
+  Draws          D{};
+  Cursor         c{};
+  bool           dead = false;
+  uint32_t       ev_total = 0;
+
+  auto take = [&]() {
+    const uint32_t nc = L.ncross, np = L.nprobe;
+    dead = false;
+    if (q < a.P_alive) {
+      load_lane(L, a.S, a.T, q);
+      init_draws(D, a.draws, a.S, q);
+      c.step = 0;
+    } else {  // born after step s on a contact site: particle ctor via repopulate (monte_carlo.h:477-486)
+      const int64_t k = q - a.P_alive, s = k / C, j = k - s * C;
+      a.S.gid[q] = a.next_gid + (uint64_t)k;
+      init_draws(D, a.draws, a.S, q);
+      if (j < a.c1_pop)
+        create_exciton(L, a.T, D, a.c1_sites, a.n_c1);
+      else
+        create_exciton(L, a.T, D, a.c2_sites, a.n_c2);
+      c.step = (int32_t)s + 1;
+    }
+    L.ncross = nc;
+    L.nprobe = np;
+    begin_step(c, L, a.dt);
+  };
+  if (have) take();
+
+  while (__any_sync(kFullMask, have)) {
+    bool finished = false;
+    if (have) {
+      if (c.step < a.nsteps && advance_contact(L, a.T, D, c)) {
+        int* h = hist + c.step * nb;
+        atomicAdd(h + y_slab(L.py, a.ymin, a.dy, a.n_seg), 1);  // monte_carlo.h:566-573
+        for (int k = 1; k < a.n_seg; ++k) {                      // monte_carlo.h:626-636
+          const int x = interface_crossing(c.oy, L.py, a.ymin + a.dy * double(k));
+          if (x) atomicAdd(h + a.n_seg + k - 1, x);
+        }
+        // repopulate_contacts: everything inside a contact slab is recycled (monte_carlo.h:463-470)
+        dead = (L.py >= a.ymin && L.py <= c1_hi) || (L.py >= c2_lo && L.py <= a.ymax);
+        ++c.step;
+        begin_step(c, L, a.dt);
+      }
+      finished = dead || (c.step >= a.nsteps) || L.stuck;
+    }
+    const unsigned fm = __ballot_sync(kFullMask, finished);
+    if (fm) {
+      if (finished) {
+        ev_total += L.nevent;
+        materialize(L, a.T);
+        store_lane(L, a.S, q);
+        a.alive[q] = dead ? 0 : 1;
+        if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
+        if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
+      }
+      unsigned long long base = 0;
+      const int          leader = __ffs(fm) - 1;
+      if (lane == leader) base = atomicAdd(a.counters + CTR_QUEUE, (unsigned long long)__popc(fm));
+      base = __shfl_sync(kFullMask, base, leader);
+      if (finished) {
+        q = (int64_t)base + __popc(fm & lt_mask);
+        have = q < W;
+        if (have) take();
+      }
+    }
+  }
+  const unsigned nc = __reduce_add_sync(kFullMask, L.ncross);
+  const unsigned np = __reduce_add_sync(kFullMask, L.nprobe);
+  const unsigned ne = __reduce_add_sync(kFullMask, ev_total);
+  if (lane == 0) {
+    if (nc) atomicAdd(a.counters + CTR_CROSS, (unsigned long long)nc);
+    if (np) atomicAdd(a.counters + CTR_PROBE, (unsigned long long)np);
+    if (ne) atomicAdd(a.counters + CTR_EVENTS, (unsigned long long)ne);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < a.nsteps * nb; k += blockDim.x)
+    if (hist[k]) atomicAdd(a.bins + k, (unsigned long long)(long long)hist[k]);
+}
+
+// initial population of monte_carlo::create_particles (monte_carlo.h:274-316): exciton e belongs to the slab whose
+// cumulative count first exceeds e and is created on a random site of that slab's (half-open) site list
+struct ContactCreateArgs {
+  Tables         T;
+  ExcitonArrays  S;
+  DrawConfig     draws;
+  int64_t        P;
+  const int64_t* count_off;  // [n_seg+1] exciton index offsets per slab
+  const int64_t* site_off;   // [n_seg+1] offsets into slab_sites
+  const int32_t* slab_sites;
+  int32_t        n_seg;
+  uint8_t*       alive;
+  int32_t*       flags;
+};
+template <typename Draws>
+__global__ void __launch_bounds__(256) create_contact_population_kernel(const ContactCreateArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.P) return;
+  int slab = 0;
+  while (slab + 1 < a.n_seg && e >= a.count_off[slab + 1]) ++slab;
+  Lane  L{};
+  Draws D{};
+  a.S.gid[e] = a.draws.first_gid + (uint64_t)e;
+  init_draws(D, a.draws, a.S, e);
+  create_exciton(L, a.T, D, a.slab_sites + a.site_off[slab], (int32_t)(a.site_off[slab + 1] - a.site_off[slab]));
+  store_lane(L, a.S, e);
+  a.S.last_events[e] = 0;
+  a.alive[e] = 1;
+  if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
+}
+
+// compaction after a contact launch: survivor i of the new list is work item src[i] of the old one
+__global__ void __launch_bounds__(256) gather_excitons_kernel(const ExcitonArrays from, const ExcitonArrays to, const uint32_t* src, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t s = src[i];
+  to.px[i] = from.px[s]; to.py[i] = from.py[s]; to.pz[i] = from.pz[s];
+  to.dx[i] = from.dx[s]; to.dy[i] = from.dy[s]; to.dz[i] = from.dz[s];
+  to.ff[i] = from.ff[s];
+  to.site[i] = from.site[s];
+  to.heading[i] = from.heading[s];
+  to.ndraw[i] = from.ndraw[s];
+  to.last_events[i] = from.last_events[s];
+  to.gid[i] = from.gid[s];
 }
 
 // ---- K1: neighbour table ---------------------------------------------------------------------------------------------------

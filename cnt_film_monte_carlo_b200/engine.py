@@ -235,11 +235,6 @@ class Engine:
         self._ck(self.L.cntmc_get_particles(self.h, _p(site), _p(pos), _p(delta), _p(ff), _p(heading), _p(ndraw)))
         return dict(site=site, pos=pos, delta=delta, ff=ff, heading=heading, ndraw=ndraw)
 
-    def old_pos(self):
-        o = np.empty((3, self.number_of_particles()))
-        self._ck(self.L.cntmc_get_old_pos(self.h, _p(o)))
-        return o
-
     def trace_enable(self, cap: int):
         self._ck(self.L.cntmc_trace_enable(self.h, cap))
         self._trace_cap = cap

@@ -222,7 +222,7 @@ class monte_carlo:
             f = self._curr_file = open(os.path.join(self._output_directory, "region_current.dat"), "w")
             f.write("interface area" + "".join("," + _sci(a) for a in area_if) + "\n\n")
             f.write("interface pos" + "".join("," + _sci(ymin + dy * i) for i in range(1, n)) + "\n\n")
-            f.write("time" + "".join(",interface%d" % (i - 1) for i in range(1, n)) + "\n")
+            f.write("time" + "".join(",interface%+d" % (i - 1) for i in range(1, n)) + "\n")  # showpos is still on in the reference
         self._curr_file.write(_sci(self.time()) + "".join("," + _sci(c / (a * dt)) for c, a in zip(cur, area_if)) + "\n")
         self._curr_file.flush()
 

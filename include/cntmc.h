@@ -138,7 +138,6 @@ double  cntmc_csr_build_seconds(const cntmc_t* h);
  * pointer may be NULL */
 int cntmc_get_particles(const cntmc_t* h, int32_t* site, double* pos, double* delta, double* ff, uint8_t* heading,
                         uint32_t* ndraw);
-int cntmc_get_old_pos(const cntmc_t* h, double* old_pos /* [3][P] */);
 
 /* record the site reached by each scattering event of the next cntmc_kubo_step call (tests only; cap events per
  * exciton).  After the step: counts [P] and sites [P][cap]. */

@@ -40,7 +40,7 @@ CASES = {
             "maximum time for kubo simulation [seconds]": 3e-12,
             "number of particles for kubo simulation": 50,
         },
-        seed=100, nsteps=300),
+        seed=100, nsteps=300, contact_steps=80),
     "wong_trimmed": dict(
         film=dict(NT=30, NP=40, a=4.0, LX=80.0, LY=50.0, seed=11),
         mc={
@@ -104,6 +104,27 @@ def make(name, case):
             subprocess.check_call([T0m.REF_BINARY, jpath], stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
             with open(os.path.join(out, "particle_dispalcement.avg.squared.dat")) as f:
                 g["ref_program_output"] = np.frombuffer(f.read().encode(), dtype=np.uint8)
+        # ---- contact mode (monte_carlo::init + the loop at main.cpp:98-106), reference code end to end ----------------
+        if case.get("contact_steps"):
+            mc2 = dict(case["mc"])
+            mc2.update({"mesh input directory": mesh, "output directory": os.path.join(tmp, "out_contacts"), "keep old results": False})
+            with open(jpath, "w") as f:
+                json.dump({"exciton monte carlo": mc2}, f)
+            t.open_contacts(jpath, seed)
+            n_seg = int(mc2["number of segments"])
+            g["contact_area"] = t.area(n_seg)
+            g["contact_c1"], g["contact_c2"] = t.contact_sites(1), t.contact_sites(2)
+            g["contact_p0_site"] = t.particles()["site"]
+            npart = [t.L.t0_num_particles()]
+            for _ in range(case["contact_steps"]):
+                t.contact_iteration(dt)
+                npart.append(t.L.t0_num_particles())
+            g["contact_num_particles"] = np.array(npart)
+            t.close()
+            for name_, key in (("population_profile.dat", "contact_pop_file"), ("region_current.dat", "contact_curr_file"),
+                               ("scatterer_statistics.dat", "contact_stat_file")):
+                with open(os.path.join(tmp, "out_contacts", name_)) as f:
+                    g[key] = np.frombuffer(f.read().encode(), dtype=np.uint8)
     mc_clean = dict(case["mc"])
     with open(os.path.join(HERE, name + ".json"), "w") as f:
         json.dump({"exciton monte carlo": mc_clean}, f, indent=1)

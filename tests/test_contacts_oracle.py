@@ -1,0 +1,53 @@
+"""Contact-driven transport (BASELINE config 5): the T1 oracle against the files written by the reference's own
+monte_carlo::init / step / save_metrics / repopulate_contacts (golden fixture), glibc draw stream."""
+import ctypes
+
+import numpy as np
+
+from oracle import t1 as T1m
+
+DT = 1e-14
+
+
+def parse(text, n_cols):
+    rows = [ln for ln in text.splitlines() if ln and ln[0] in "+-"]
+    return np.array([[float(v) for v in ln.split(",")] for ln in rows]).reshape(len(rows), n_cols + 1)
+
+
+def test_contact_run_reproduces_reference_files(golden_small):
+    g = golden_small
+    n_seg = int(g.mc["number of segments"])
+    t = T1m.T1()
+    t.draws_glibc()
+    ctypes.CDLL("libc.so.6").srandom(g.seed)
+    t.contacts_init(g.mc, g.pos_nm, g.orient)
+    assert np.array_equal(t.area(), g.z["contact_area"])       # incl. the reference's min-or-max quirk (negative areas)
+    assert np.array_equal(t.contact_sites(1), g.z["contact_c1"]) and np.array_equal(t.contact_sites(2), g.z["contact_c2"])
+    assert np.array_equal(t.particles()["site"], g.z["contact_p0_site"])
+    pop_ref = parse(bytes(g.z["contact_pop_file"]).decode(), n_seg)
+    cur_ref = parse(bytes(g.z["contact_curr_file"]).decode(), n_seg - 1)
+    area = t.area()
+    dom = t.domain()
+    dy = (dom[4] - dom[1]) / n_seg
+    area_if = (area[:-1] + area[1:]) / 2
+    nsteps = len(pop_ref)
+    assert nsteps == len(g.z["contact_num_particles"]) - 1
+    for s in range(nsteps):
+        pop, cur = t.contact_iteration(DT)
+        assert t.L.t1_num_particles(t.h) == g.z["contact_num_particles"][s + 1]
+        # the reference prints count / (area * dy) and net / (area_if * dt) with 7 significant digits
+        assert np.allclose(pop / (area * dy), pop_ref[s, 1:], rtol=2e-6, atol=0), s
+        assert np.allclose(cur / (area_if * DT), cur_ref[s, 1:], rtol=2e-6, atol=0), s
+        assert pop.sum() == g.z["contact_num_particles"][s]     # everybody alive during the step is counted once
+
+
+def test_philox_contact_run_is_reproducible_and_conserves_excitons(golden_small):
+    g = golden_small
+    runs = []
+    for _ in range(2):
+        t = T1m.T1()
+        t.draws_philox(11)
+        t.contacts_init(g.mc, g.pos_nm, g.orient, c1_pop=300, c2_pop=40)
+        hist = [t.contact_iteration(DT) for _ in range(40)]
+        runs.append((np.array([h[0] for h in hist]), np.array([h[1] for h in hist])))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
