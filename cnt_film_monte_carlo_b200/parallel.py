@@ -1,0 +1,50 @@
+"""Sharding of the exciton population over the GPUs of one box.
+
+Excitons never interact and all tables are read-only while stepping, so rank r of W simply owns the excitons with
+global ids [first, first + count): their counter-based streams are keyed by global id, hence every trajectory is
+the same for any W.  The only exchange is one all-reduce (sum) of the per-interval [sum dx^2, sum dy^2, sum dz^2, hops]
+rows (Green-Kubo) or of the integer population / current bins (contacts) per engine call -- a few kilobytes over
+NCCL/NVLink.  torch.distributed is the plumbing; nothing here computes.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """(first global id, count) of rank's share of `total` excitons; the first total % world ranks hold one more."""
+    base, extra = divmod(int(total), int(world))
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def allreduce_sums(local, group=None):
+    """Sum a [nsteps][k] array of un-normalised sums over all ranks.  numpy in, numpy out (gloo, CPU tests); a CUDA
+    torch tensor is reduced in place over NCCL and returned."""
+    import torch
+    import torch.distributed as dist
+
+    if isinstance(local, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(local))
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(t, group=group)
+        return t.numpy()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(local, group=group)
+    return local
+
+
+class ShardedKubo:
+    """One rank's part of a Green-Kubo run: `stepper(dt, nsteps)` must return this rank's [nsteps][3] sums of squared
+    displacements (e.g. ``lambda dt, n: engine.kubo_step(dt, n) * count``)."""
+
+    def __init__(self, total_excitons: int, rank: int, world: int, group=None):
+        self.total, self.rank, self.world, self.group = int(total_excitons), rank, world, group
+        self.first, self.count = shard_range(total_excitons, rank, world)
+
+    def msd(self, local_sums: np.ndarray) -> np.ndarray:
+        """Ensemble average over the WHOLE population from this rank's local sums (monte_carlo.cpp:402-404)."""
+        return allreduce_sums(np.asarray(local_sums, np.float64), self.group) / float(self.total)
