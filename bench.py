@@ -48,17 +48,45 @@ def mc_block(P):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons of one GPU, polled through NVML every 25 ms while the timed region runs
+    (falls back to `nvidia-smi -lms 100`, the recipe of B200_PROFILING.md, if NVML cannot be loaded)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop_flag, self.thread = index, [], None, False, None
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                for name, bit in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.025)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))]
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -69,14 +97,17 @@ class ClockSampler:
             self.rows.append([t.strip() for t in line.split(",")])
 
     def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+            self.sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+            self.mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.reasons = {n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def measured_hbm_peak():
@@ -236,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
         peak, which = measured_hbm_peak()
         achieved = abytes / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": which, "kernel": "kubo_flat_kernel",
+                "traffic": None, "peak_source": which, "kernel": "kubo_kernel",
                 "kernel_ms_per_launch": k_ms / max(1, k_n), "kernel_share_of_step": k_ms / eng.last_step_ms(),
                 "bytes_per_hop": abytes / max(1, hops), "probes_per_hop": probes / max(1, hops),
                 "crossings_per_hop": crossings / max(1, hops), "hops_per_launch": hops / max(1, k_n)}
@@ -305,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--excitons", type=int, default=1_000_000, help="excitons per GPU")
@@ -315,7 +346,7 @@ def main():
     ap.add_argument("--occupancy", type=int, default=5, help="resident 128-thread blocks per SM of the hop kernel (4, 5, 6, 8)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-excitons", type=int, default=8000)
-    ap.add_argument("--cpu-intervals", type=int, default=400)
+    ap.add_argument("--cpu-intervals", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
