@@ -125,65 +125,74 @@ def algorithmic_bytes(hops, probes, crossings, P, launches):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(P, intervals, threads):
-    """The reference's own particle loop (libt0.so: its particle.cpp/scatterer.cpp compiled from /root/reference) on
-    the C2 film; falls back to the oracle port if that library did not travel.  Returns (hops, seconds, kind)."""
-    import tempfile
-    from cnt_film_monte_carlo_b200 import film
-    from oracle import t0 as T0m, t1 as T1m
+class CpuReference:
+    """The reference's own particle loop, set up once; each step() advances the same simulation by `intervals`."""
 
-    pos, ori = film.film(**film.CONFIG_FILMS["C2"])
-    mc = mc_block(P)
-    if T0m.available():
-        with tempfile.TemporaryDirectory() as tmp:
-            mesh = os.path.join(tmp, "mesh")
+    def __init__(self, P, threads):
+        import tempfile
+        from cnt_film_monte_carlo_b200 import film
+        from oracle import t0 as T0m, t1 as T1m
+
+        pos, ori = film.film(**film.CONFIG_FILMS["C2"])
+        mc = mc_block(P)
+        self.kind = "reference" if T0m.available() else "port"
+        if self.kind == "reference":
+            self.tmp = tempfile.TemporaryDirectory()
+            mesh = os.path.join(self.tmp.name, "mesh")
             film.write_mesh(mesh, pos, ori)
-            mc.update({"mesh input directory": mesh, "output directory": os.path.join(tmp, "out"), "keep old results": False})
-            jpath = os.path.join(tmp, "input.json")
+            mc.update({"mesh input directory": mesh, "output directory": os.path.join(self.tmp.name, "out"), "keep old results": False})
+            jpath = os.path.join(self.tmp.name, "input.json")
             with open(jpath, "w") as f:
                 json.dump({"exciton monte carlo": mc}, f)
-            t = T0m.T0()
-            t.set_threads(threads)
-            t.open(jpath, 100)           # kubo_init incl. set_max_rate on all cores
-            t.create_particles_verbatim()
-            d0 = t.total_draws()
+            self.t = T0m.T0()
+            self.t.set_threads(threads)
+            self.t.open(jpath, 100)
+            self.t.create_particles_verbatim()
+            self.cores = threads
+        else:
+            self.t = T1m.T1()
+            self.t.kubo_init(mc, pos, ori)
+            self.t.draws_glibc()
+            self.t.create_particles(P)
+            self.cores = 1
+
+    def step(self, intervals):
+        """(hops, seconds) of `intervals` x kubo_step(1e-13)."""
+        if self.kind == "reference":
+            d0 = self.t.total_draws()
             t0 = time.perf_counter()
-            reinj = t.kubo_step_omp(DT, intervals)   # monte_carlo::kubo_step's OpenMP loop (monte_carlo.cpp:319-342)
+            reinj = self.t.kubo_step_omp(DT, intervals)
             sec = time.perf_counter() - t0
-            hops = (t.total_draws() - d0 - reinj) // 2   # 2 draws per event (scatterer.cpp:17, scatterer.h:76)
-            t.close()
-        return hops, sec, "reference"
-    s = T1m.T1()
-    s.kubo_init(mc, pos, ori)
-    s.draws_glibc()
-    s.create_particles(P)
-    t0 = time.perf_counter()
-    s.kubo_step(DT, intervals, want_msd=False)   # reference-faithful: neighbour list rebuilt on every hop, 1 thread
-    return s.hops(), time.perf_counter() - t0, "port"
+            return (self.t.total_draws() - d0 - reinj) // 2, sec
+        h0 = self.t.hops()
+        t0 = time.perf_counter()
+        self.t.kubo_step(DT, intervals, want_msd=False)
+        return self.t.hops() - h0, time.perf_counter() - t0
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    P, intervals = args.cpu_excitons, args.cpu_intervals
-    vals = []
-    kind = "reference"
-    for i in range(args.warmup + args.steps):
-        hops, sec, kind = cpu_reference_run(P, intervals, threads)
-        if i >= args.warmup:
-            vals.append((hops, sec))
+    ref = CpuReference(args.cpu_excitons, os.cpu_count() or 1)
+    # size the per-step sample so that warm-up + timed steps take about args.cpu_budget seconds in total
+    hops, sec = ref.step(20)
+    rate = max(hops / sec, 1.0)
+    per_interval = max(sec / 20, 1e-6)
+    intervals = int(min(2000, max(10, args.cpu_budget / per_interval / (args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        ref.step(intervals)
+    vals = [ref.step(intervals) for _ in range(args.steps)]
     hops = sum(v[0] for v in vals)
     sec = sum(v[1] for v in vals)
     value = hops / sec
-    cores = threads if kind == "reference" else 1
-    sample = "%d excitons x %d intervals of 1e-13 s per step on the C2 film" % (P, intervals)
+    sample = "%d excitons x %d intervals of 1e-13 s per step on the C2 film, reference built against an Armadillo stand-in" % (
+        args.cpu_excitons, intervals)
     print(json.dumps({
         "impl": "reference", "metric": "exciton hops/sec", "value": value, "unit": "hops/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "dt_s": DT, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "hops/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "hops/s", "cores": ref.cores, "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": "hops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -307,10 +316,13 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        hops_c, sec_c, kind = cpu_reference_run(args.cpu_excitons, args.cpu_intervals, os.cpu_count() or 1)
-        cpu = {"value": hops_c / sec_c, "unit": "hops/s", "cores": (os.cpu_count() or 1) if kind == "reference" else 1,
-               "kind": kind, "sample": "%d excitons x %d intervals of 1e-13 s on the C2 film (%.1f s)" % (
-                   args.cpu_excitons, args.cpu_intervals, sec_c)}
+        ref = CpuReference(args.cpu_excitons, os.cpu_count() or 1)
+        h20, s20 = ref.step(20)
+        n_int = int(min(4000, max(20, 15.0 / max(s20 / 20, 1e-6))))   # about 15 s of CPU work
+        hops_c, sec_c = ref.step(n_int)
+        cpu = {"value": hops_c / sec_c, "unit": "hops/s", "cores": ref.cores, "kind": ref.kind,
+               "sample": "%d excitons x %d intervals of 1e-13 s on the C2 film (%.1f s), reference built against an Armadillo stand-in" % (
+                   args.cpu_excitons, n_int, sec_c)}
 
     if rank == 0:
         launches_per_step = eng.last_step_launches()
@@ -346,7 +358,7 @@ def main():
     ap.add_argument("--occupancy", type=int, default=5, help="resident 128-thread blocks per SM of the hop kernel (4, 5, 6, 8)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-excitons", type=int, default=8000)
-    ap.add_argument("--cpu-intervals", type=int, default=1500)
+    ap.add_argument("--cpu-budget", type=float, default=100.0, help="seconds of CPU work for the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
