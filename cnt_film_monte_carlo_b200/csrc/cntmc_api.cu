@@ -163,8 +163,12 @@ struct cntmc_handle {
   DevBuf<double>   r_logs;
 
   // reductions, diagnostics
-  DevBuf<double>             d_partial, d_sums, d_stage;
-  DevBuf<uint32_t>           d_stage_ev;
+  DevBuf<double>             d_partial, d_sums;
+  DevBuf<StageRec>           d_stage;
+  DevBuf<uint32_t>           d_list[2][kClasses], d_list_count[2];
+  DevBuf<unsigned long long> d_list_head;
+  int                        cur_list = 0;
+  bool                       have_lists = false;
   DevBuf<int32_t>            d_flags;
   DevBuf<unsigned long long> d_counters;
   DevBuf<int32_t>            d_trace_sites, d_trace_counts;
@@ -175,12 +179,16 @@ struct cntmc_handle {
   int64_t     last_launches = 0;
 
   // tuning
-  int64_t opt_chunk = 64;   // time steps per launch
-  int64_t opt_sort = 1;     // regroup excitons by activity between launches
+  int64_t opt_chunk = 8;      // time steps per launch
+  int64_t opt_sort = 1;       // (kept for compatibility; activity classes replaced the sort)
+  int64_t opt_hot_pct = 30;   // share of the blocks that serve the most active classes first
+  int64_t opt_park_min = 8;   // lanes that must want the warp's minority operation before it runs ...
+  int64_t opt_park_wait = 4;  // ... unless it has been waiting this many iterations
   int64_t opt_block = 128;  // threads per block of the hop kernel
   int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
   int64_t opt_stage_mb = 4096;  // cap on the (step, exciton) staging buffer; shortens the launches if needed
   int     sm_count = 0;
+  int64_t opt_stats = 0;         // count cumulative-rate probes and chain crossings (roofline bookkeeping)
   int64_t opt_time_kernels = 0;  // CUDA events around every hop-kernel launch (bench.py's roofline figure)
   std::vector<cudaEvent_t> kernel_events;
   double  kernel_ms = 0;
@@ -412,6 +420,7 @@ void create_common(cntmc_t* h, int64_t P) {
   h->alloc_excitons(P);
   h->P = P;
   h->have_events = false;
+  h->have_lists = false;
   h->time = 0;
   h->hops = h->reinjections = 0;
   h->crossings = h->probes = 0;
@@ -426,14 +435,23 @@ void create_common(cntmc_t* h, int64_t P) {
 
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 
+template <typename Draws, bool kInstr>
+void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) {
+  switch (h->opt_occupancy) {
+    case 4: kubo_kernel<Draws, 4, kInstr><<<grid, 128, 0, st>>>(a); break;
+    case 6: kubo_kernel<Draws, 6, kInstr><<<grid, 128, 0, st>>>(a); break;
+    case 7: kubo_kernel<Draws, 7, kInstr><<<grid, 128, 0, st>>>(a); break;
+    case 8: kubo_kernel<Draws, 8, kInstr><<<grid, 128, 0, st>>>(a); break;
+    default: kubo_kernel<Draws, 5, kInstr><<<grid, 128, 0, st>>>(a); break;
+  }
+}
 template <typename Draws>
 void launch_kubo(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) {
-  switch (h->opt_occupancy) {
-    case 4: kubo_kernel<Draws, 4><<<grid, 128, 0, st>>>(a); break;
-    case 8: kubo_kernel<Draws, 8><<<grid, 128, 0, st>>>(a); break;
-    case 6: kubo_kernel<Draws, 6><<<grid, 128, 0, st>>>(a); break;
-    default: kubo_kernel<Draws, 5><<<grid, 128, 0, st>>>(a); break;
-  }
+  // the instrumented variant (site traces, probe / crossing counters) runs only when somebody asked for its output
+  if (h->trace_cap > 0 || h->opt_stats)
+    launch_kubo_i<Draws, true>(h, a, grid, st);
+  else
+    launch_kubo_i<Draws, false>(h, a, grid, st);
 }
 
 // nsteps x kubo_step on the device; sums -> dev_sums[nsteps][4]
@@ -449,42 +467,55 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   // time steps per launch: the option, capped so that the (step, exciton) staging buffer stays within its budget
-  const int64_t by_budget = std::max<int64_t>(1, (h->opt_stage_mb << 20) / (28 * h->P));
+  const int64_t by_budget = std::max<int64_t>(1, (h->opt_stage_mb << 20) / ((int64_t)sizeof(StageRec) * h->P));
   const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({h->opt_chunk, by_budget, nsteps}));
   // persistent grid: as many 128-thread blocks as the SMs hold at the compiled occupancy, never more than needed
   const int64_t  want = (h->P + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)h->sm_count * h->opt_occupancy);
-  h->d_stage.alloc((size_t)3 * (size_t)chunk * (size_t)h->P);
-  h->d_stage_ev.alloc((size_t)chunk * (size_t)h->P);
+  h->d_stage.alloc((size_t)chunk * (size_t)h->P);
   h->d_partial.alloc((size_t)chunk * kStageSplits * 4);
+  // activity-class lists, double-buffered: [cur] is read by a launch, [1-cur] is filled by it
+  for (int b = 0; b < 2; ++b) {
+    for (int c = 0; c < kClasses; ++c) h->d_list[b][c].alloc((size_t)h->P);
+    h->d_list_count[b].alloc(kClasses);
+  }
+  h->d_list_head.alloc(kClasses);
+  auto lists = [&](int read_buf) {
+    ClassLists q{};
+    for (int c = 0; c < kClasses; ++c) {
+      q.list[c] = h->d_list[read_buf][c].p;
+      q.next_list[c] = h->d_list[1 - read_buf][c].p;
+    }
+    q.count = h->d_list_count[read_buf].p;
+    q.next_count = h->d_list_count[1 - read_buf].p;
+    q.head = h->d_list_head.p;
+    return q;
+  };
   h->last_launches = 0;
   CUDA_CHECK(cudaEventRecord(h->ev0, st));
+  if (!h->have_lists) {  // population just created or uploaded: file everything once
+    CUDA_CHECK(cudaMemsetAsync(h->d_list_count[h->cur_list].p, 0, kClasses * sizeof(uint32_t), st));
+    classify_kernel<<<(unsigned)((h->P + 255) / 256), 256, 0, st>>>(h->T, h->ex.site.p, h->P, dt, lists(1 - h->cur_list));
+    CUDA_CHECK(cudaGetLastError());
+    h->have_lists = true;
+    h->last_launches += 1;
+  }
   for (int64_t done = 0; done < nsteps; done += chunk) {
-    const int       n = (int)std::min(chunk, nsteps - done);
-    const uint32_t* order = nullptr;
-    if (h->opt_sort && h->have_events) {
-      // queue order: most active excitons (events in the previous launch) first
-      iota_kernel<<<(unsigned)((h->P + 255) / 256), 256, 0, st>>>(h->e_iota.p, h->P);
-      size_t bytes = 0;
-      cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, h->ex.events.p, h->e_keys_out.p, h->e_iota.p, h->e_perm.p,
-                                                (int)h->P, 0, 32, st);
-      h->sort_tmp.alloc(bytes);
-      CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(h->sort_tmp.p, bytes, h->ex.events.p, h->e_keys_out.p, h->e_iota.p,
-                                                           h->e_perm.p, (int)h->P, 0, 32, st));
-      order = h->e_perm.p;
-      h->last_launches += 1;
-    }
-    set_u64_kernel<<<1, 1, 0, st>>>(h->d_counters.p + CTR_QUEUE, (unsigned long long)grid * 128ull);
+    const int n = (int)std::min(chunk, nsteps - done);
+    CUDA_CHECK(cudaMemsetAsync(h->d_list_head.p, 0, kClasses * sizeof(unsigned long long), st));
+    CUDA_CHECK(cudaMemsetAsync(h->d_list_count[1 - h->cur_list].p, 0, kClasses * sizeof(uint32_t), st));
     KuboArgs a{};
     a.T = h->T;
     a.S = h->arrays();
     a.draws = h->draws;
-    a.order = order;
+    a.q = lists(h->cur_list);
+    a.hot_blocks = (int32_t)((int64_t)grid * h->opt_hot_pct / 100);
+    a.park_min = (int32_t)h->opt_park_min;
+    a.park_wait = (int32_t)h->opt_park_wait;
     a.P = h->P;
     a.dt = dt;
     a.nsteps = n;
     a.stage = h->d_stage.p;
-    a.stage_ev = h->d_stage_ev.p;
     a.trace_sites = h->trace_cap ? h->d_trace_sites.p : nullptr;
     a.trace_counts = h->trace_cap ? h->d_trace_counts.p : nullptr;
     a.trace_cap = h->trace_cap;
@@ -504,12 +535,12 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
       launch_kubo<PhiloxDraws>(h, a, grid, st);
     CUDA_CHECK(cudaGetLastError());
     if (k1) CUDA_CHECK(cudaEventRecord(k1, st));
-    reduce_stage_kernel<<<dim3((unsigned)n, kStageSplits), 256, 0, st>>>(h->d_stage.p, h->d_stage_ev.p, h->P, n, h->d_partial.p);
+    h->cur_list = 1 - h->cur_list;
+    reduce_stage_kernel<<<dim3((unsigned)n, kStageSplits), 256, 0, st>>>(h->d_stage.p, h->P, n, h->d_partial.p);
     CUDA_CHECK(cudaGetLastError());
     finish_sums_kernel<<<(n * 4 + 127) / 128, 128, 0, st>>>(h->d_partial.p, n, dev_sums + done * 4);
     CUDA_CHECK(cudaGetLastError());
-    h->last_launches += 4;
-    h->have_events = true;
+    h->last_launches += 3;
   }
   CUDA_CHECK(cudaEventRecord(h->ev1, st));
   for (int64_t s = 0; s < nsteps; ++s) h->time += dt;  // monte_carlo.cpp:341, one addition per step
@@ -729,7 +760,7 @@ int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P,
     use_device(h);
     cudaStream_t st = h->stream;
     if (P > h->capacity) h->alloc_excitons(P);
-    if (P != h->P) h->have_events = false;
+    h->have_lists = false;  // the uploaded population has not been filed under activity classes yet
     h->P = P;
     const size_t n = (size_t)P;
     h->ex.site.upload(site, n, st);
@@ -1101,12 +1132,23 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "block") {
       require(value == 32 || value == 64 || value == 128, "block must be 32, 64 or 128");
       h->opt_block = value;
+    } else if (k == "hot_pct") {
+      require(value >= 0 && value <= 100, "hot_pct must be in [0, 100]");
+      h->opt_hot_pct = value;
+    } else if (k == "park_min") {
+      require(value >= 1 && value <= 32, "park_min must be in [1, 32]");
+      h->opt_park_min = value;
+    } else if (k == "park_wait") {
+      require(value >= 0 && value <= 1000, "park_wait must be in [0, 1000]");
+      h->opt_park_wait = value;
     } else if (k == "occupancy") {
-      require(value == 4 || value == 5 || value == 6 || value == 8, "occupancy must be 4, 5, 6 or 8 blocks per SM");
+      require(value >= 4 && value <= 8, "occupancy must be 4 to 8 blocks per SM");
       h->opt_occupancy = value;
     } else if (k == "stage_mb") {
       require(value >= 1, "stage_mb must be positive");
       h->opt_stage_mb = value;
+    } else if (k == "stats") {
+      h->opt_stats = value ? 1 : 0;
     } else if (k == "time_kernels") {
       h->opt_time_kernels = value ? 1 : 0;
     } else {
@@ -1120,6 +1162,9 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "sort") return h->opt_sort;
   if (k == "block") return h->opt_block;
   if (k == "occupancy") return h->opt_occupancy;
+  if (k == "hot_pct") return h->opt_hot_pct;
+  if (k == "park_min") return h->opt_park_min;
+  if (k == "park_wait") return h->opt_park_wait;
   if (k == "stage_mb") return h->opt_stage_mb;
   return -1;
 }

@@ -2,7 +2,8 @@
 //
 //   K1  csr_rows_kernel<false/true>   neighbour table: scatterer::find_neighbors of every site, once, as CSR
 //   K4  create_excitons_kernel        monte_carlo::kubo_create_particles / create_particles / repopulate
-//   K2  kubo_kernel                   nsteps x monte_carlo::kubo_step for every exciton (persistent warps, lanes refill)
+//   K2  kubo_kernel                   nsteps x monte_carlo::kubo_step for every exciton (persistent warps, lanes refill
+//                                     from activity-class lists)
 //       reduce_stage_kernel           per-(step, exciton) squared displacements -> [nsteps][4] sums, fixed order
 //
 // All arithmetic is FP64 / integer; there is no dense contraction anywhere on this path, so tensor cores (tcgen05)
@@ -108,16 +109,77 @@ __global__ void __launch_bounds__(256) create_excitons_kernel(const CreateArgs a
 }
 
 // ---- K2: the hop kernel, Green-Kubo flavour -------------------------------------------------------------------------------
+// Activity classes.  Exciton activity is extremely skewed (on the C2 film the median exciton scatters twice in 64 steps,
+// the 99th percentile 1400 times: a few excitons sit in traps between closely crossing tubes) and it is predictable from
+// the state: Gamma(site) * dt = expected events per step if the exciton stays where it is.  When a lane stores an
+// exciton it files it under one of four classes; the next launch hands classes out from the hot end to "hot" blocks
+// and from the cold end to "cold" blocks, so that warps mostly hold excitons that run the same branch of the loop.
+constexpr int kClasses = 4;
+__device__ __forceinline__ int activity_class(double expected_events_per_step) {
+  return expected_events_per_step >= 8.0 ? 3 : expected_events_per_step >= 1.0 ? 2 : expected_events_per_step >= 0.125 ? 1 : 0;
+}
+struct ClassLists {
+  const uint32_t*     list[kClasses];       // excitons of each class, filed by the previous launch
+  const uint32_t*     count;                // [kClasses]
+  unsigned long long* head;                 // [kClasses] next unassigned position of each list
+  uint32_t*           next_list[kClasses];  // being filled for the next launch
+  uint32_t*           next_count;           // [kClasses]
+};
+
+// file exciton e of the lanes flagged `mine` under their class `cls` (warp-aggregated append; call with the whole warp)
+__device__ __forceinline__ void file_excitons(const ClassLists& q, bool mine, int cls, uint32_t e, int lane, unsigned lt_mask) {
+#pragma unroll
+  for (int c = 0; c < kClasses; ++c) {
+    const unsigned m = __ballot_sync(0xffffffffu, mine && cls == c);
+    if (m) {
+      uint32_t  base = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(q.next_count + c, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (mine && cls == c) q.next_list[c][base + __popc(m & lt_mask)] = e;
+    }
+  }
+}
+// hand an exciton to every lane that `want`s one, from the two classes of the warp's current role: hot warps serve
+// classes 3 then 2, cold warps classes 0 then 1 (call with the whole warp).  Returns false for lanes left without work.
+__device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, bool hot_role, int lane, unsigned lt_mask, int64_t& e) {
+  bool     got = false;
+  unsigned need = __ballot_sync(0xffffffffu, want);
+  for (int k = 0; k < 2 && need; ++k) {
+    const int          c = hot_role ? kClasses - 1 - k : k;
+    const int          n = __popc(need), leader = __ffs(need) - 1;
+    const long long    cnt = (long long)q.count[c];
+    unsigned long long base = 0;
+    if (lane == leader) base = (cnt > 0) ? atomicAdd(q.head + c, (unsigned long long)n) : (unsigned long long)cnt;
+    base = __shfl_sync(0xffffffffu, base, leader);
+    const long long avail = cnt - (long long)base;
+    if (want && !got) {
+      const int rank = __popc(need & lt_mask);
+      if ((long long)rank < avail) {
+        e = (int64_t)q.list[c][base + (unsigned long long)rank];
+        got = true;
+      }
+    }
+    need = __ballot_sync(0xffffffffu, want && !got);
+  }
+  return got;
+}
+
+struct alignas(32) StageRec {  // one full 32-byte sector per (step, exciton)
+  double dx2, dy2, dz2, events;
+};
+
 struct KuboArgs {
   Tables              T;
   ExcitonArrays       S;
   DrawConfig          draws;
-  const uint32_t*     order;  // queue position -> exciton (null = identity); most active excitons first
+  ClassLists          q;
+  int32_t             hot_blocks;  // blocks [0, hot_blocks) serve the active classes first
+  int32_t             park_min, park_wait;  // see the loop of kubo_kernel
   int64_t             P;
   double              dt;
   int32_t             nsteps;
-  double*             stage;     // [3][nsteps][P]: dx^2, dy^2, dz^2 of the exciton at queue position q after step s
-  uint32_t*           stage_ev;  // [nsteps][P]: scattering events of that exciton in that step
+  StageRec*           stage;  // [nsteps][P] by exciton index
   int32_t*            trace_sites;
   int32_t*            trace_counts;
   int32_t             trace_cap;
@@ -125,110 +187,163 @@ struct KuboArgs {
   unsigned long long* counters;
 };
 
-// Persistent warps; every lane owns one exciton at a time and carries it through all nsteps time steps of the launch,
-// then takes the next unassigned exciton from a global queue (one warp-aggregated atomic).  The queue is ordered by the
-// activity seen in the previous launch, most active first, so the long sequential chains of trapped excitons (thousands
-// of events while the median exciton has two) start at once and the short ones fill in behind them.
+// Persistent warps; every lane owns one exciton at a time, carries it through all nsteps time steps of the launch, files
+// it under its activity class for the next launch and takes another one (see ClassLists).
 //
 // The loop is flat: an iteration moves every busy lane forward by one scattering event or by the end of one time step,
 // whichever comes first for that lane; lanes of a warp are in general in different time steps of different excitons.
-// Nothing in the loop needs a barrier, shared memory or a floating-point atomic: when a lane ends a step it writes
-// its squared displacement to a (step, queue position) slot, and reduce_stage_kernel sums the slots in a fixed order
-// afterwards, so the ensemble sums do not depend on which lane happened to process which exciton.
-template <typename Draws, int kMinBlocks>
+// Nothing in the loop needs a barrier, shared memory or a floating-point atomic: when a lane ends a step it writes its
+// squared displacement to the (step, exciton) record, and reduce_stage_kernel sums the records in a fixed order
+// afterwards, so the ensemble sums do not depend on which lane happened to process which exciton, nor on any tuning
+// option.
+// kInstr adds what only tests and the roofline bookkeeping need (site traces, probe / crossing counters).
+template <typename Draws, int kMinBlocks, bool kInstr>
 __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a) {
-  const int      lane = threadIdx.x & 31;
+  // The displacement accumulator and the position at the start of the step are only touched when a time step ends;
+  // they live in shared memory (one slot per thread) so that the event path does not carry 12 registers of them.
+  __shared__ double s_delta[3][128], s_old[3][128];
+  const int      tid = threadIdx.x, lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  int64_t        q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // first assignment is static
-  bool           have = q < a.P;
-  int64_t        e = 0;
+  const bool     hot_role = (int)blockIdx.x < a.hot_blocks;
+  uint32_t       e = 0;
   Lane           L{};
   Draws          D{};
-  Cursor         c{};
+  double         dt_rem = 0.0;
+  int32_t        step = 0;
+  uint32_t       ev0 = 0;
   int32_t*       trace = nullptr;
   int32_t        trace_base = 0;
-  const size_t   plane = (size_t)a.nsteps * (size_t)a.P;
 
-  auto take = [&]() {
-    e = a.order ? (int64_t)a.order[q] : q;
+  auto start = [&]() {
     const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject;
-    load_lane(L, a.S, a.T, e);
+    load_lane(L, a.S, a.T, (int64_t)e);
     L.ncross = nc;
     L.nprobe = np;
     L.nreinject = nr;
-    init_draws(D, a.draws, a.S, e);
-    c.step = 0;
-    begin_step(c, L, a.dt);
-    if (a.trace_sites) {  // the trace continues where the previous launch stopped
+    init_draws(D, a.draws, a.S, (int64_t)e);
+    step = 0;
+    dt_rem = a.dt;
+    ev0 = 0;
+    s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
+    s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;  // _old_pos = _pos (particle.cpp:59)
+    if (kInstr && a.trace_sites) {  // the trace continues where the previous launch stopped
       trace_base = a.trace_counts[e];
-      trace = a.trace_sites + e * (int64_t)a.trace_cap + trace_base;
+      trace = a.trace_sites + (int64_t)e * a.trace_cap + trace_base;
     }
   };
-  if (have) take();
-
-  while (__any_sync(kFullMask, have)) {
-    bool finished = false;
+  // A warp keeps to one role so that its lanes run the same branch of the loop most of the time (hot: scattering
+  // events, cold: chain walks and step ends); it changes role only once, when all its lanes have run dry.
+  bool role = hot_role;
+  for (int pass = 0; pass < 2; ++pass, role = !role) {
+    int64_t e64 = 0;
+    bool    have = take_exciton(a.q, true, role, lane, lt_mask, e64);
     if (have) {
-      if (advance(L, a.T, D, c, trace, (uint32_t)(a.trace_cap - trace_base))) {
-        const size_t slot = (size_t)c.step * (size_t)a.P + (size_t)q;
-        // streaming stores: written once, read once by the reduction, must not evict the tables from L2
-        __stcs(a.stage + slot, L.dx * L.dx);  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
-        __stcs(a.stage + plane + slot, L.dy * L.dy);
-        __stcs(a.stage + 2 * plane + slot, L.dz * L.dz);
-        __stcs(a.stage_ev + slot, L.nevent - c.ev0);
-        ++c.step;
-        begin_step(c, L, a.dt);
-      }
-      finished = (c.step >= a.nsteps) || L.stuck;
+      e = (uint32_t)e64;
+      start();
     }
-    const unsigned fm = __ballot_sync(kFullMask, finished);
-    if (fm) {
-      if (finished) {
-        materialize(L, a.T);
-        store_lane(L, a.S, e);
-        if (a.trace_counts) a.trace_counts[e] = trace_base + (int32_t)L.nevent;
-        if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
-        if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
+    int waited = 0;
+    while (__any_sync(kFullMask, have)) {
+      bool finished = false;
+      // The next operation of a lane is known before it starts: a scattering event if the free flight ends inside the
+      // step, the end of the step otherwise.  The two kinds run different code, so the kind that is in the minority of
+      // this warp is parked until enough lanes want it (or it has waited park_wait iterations, or nothing else can
+      // run); the majority kind of the warp's role runs every iteration.
+      const bool     is_event = have && (L.ff <= dt_rem);  // particle.cpp:62
+      const unsigned mE = __ballot_sync(kFullMask, is_event), mS = __ballot_sync(kFullMask, have && !is_event);
+      const int      nE = __popc(mE), nS = __popc(mS);
+      bool           runE, runS;
+      if (role) {
+        runE = nE > 0;
+        runS = nS > 0 && (nS >= a.park_min || nE == 0 || waited >= a.park_wait);
+        waited = (nS > 0 && !runS) ? waited + 1 : 0;
+      } else {
+        runS = nS > 0;
+        runE = nE > 0 && (nE >= a.park_min || nS == 0 || waited >= a.park_wait);
+        waited = (nE > 0 && !runE) ? waited + 1 : 0;
       }
-      unsigned long long base = 0;
-      const int          leader = __ffs(fm) - 1;
-      if (lane == leader) base = atomicAdd(a.counters + CTR_QUEUE, (unsigned long long)__popc(fm));
-      base = __shfl_sync(kFullMask, base, leader);
-      if (finished) {
-        q = (int64_t)base + __popc(fm & lt_mask);
-        have = q < a.P;
-        if (have) take();
+      if (have && (is_event ? runE : runS)) {
+        const double t = is_event ? L.ff : dt_rem;
+        const Leg    leg = fly(L, a.T, t);
+        if (is_event) {
+          dt_rem -= t;  // particle.cpp:63
+          after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u);
+        } else {
+          L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
+          after_flight_step_end(L, a.T, D, leg, t, s_old[0][tid], s_old[1][tid], s_old[2][tid]);
+          // streaming stores: written once, read once by the reduction, must not evict the tables from L2
+          double2* rec = reinterpret_cast<double2*>(a.stage + ((size_t)step * (size_t)a.P + (size_t)e));
+          __stcs(rec, make_double2(L.dx * L.dx, L.dy * L.dy));  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
+          __stcs(rec + 1, make_double2(L.dz * L.dz, (double)(L.nevent - ev0)));
+          s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
+          s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;
+          ++step;
+          dt_rem = a.dt;
+          ev0 = L.nevent;
+        }
+        finished = (step >= a.nsteps) || L.stuck;
+      }
+      if (__any_sync(kFullMask, finished)) {
+        int cls = 0;
+        if (finished) {
+          materialize(L, a.T);
+          L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
+          store_lane(L, a.S, (int64_t)e);
+          cls = activity_class(load_hop(a.T.site + L.site).total * a.dt);
+          if (kInstr && a.trace_counts) a.trace_counts[e] = trace_base + (int32_t)L.nevent;
+          if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
+          if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
+        }
+        file_excitons(a.q, finished, cls, e, lane, lt_mask);
+        const bool got = take_exciton(a.q, finished, role, lane, lt_mask, e64);
+        if (finished) {
+          have = got;
+          if (have) {
+            e = (uint32_t)e64;
+            start();
+          }
+        }
       }
     }
   }
 
-  const unsigned nc = __reduce_add_sync(kFullMask, L.ncross);
-  const unsigned np = __reduce_add_sync(kFullMask, L.nprobe);
   const unsigned nr = __reduce_add_sync(kFullMask, L.nreinject);
-  if (lane == 0) {
-    if (nc) atomicAdd(a.counters + CTR_CROSS, (unsigned long long)nc);
-    if (np) atomicAdd(a.counters + CTR_PROBE, (unsigned long long)np);
-    if (nr) atomicAdd(a.counters + CTR_REINJECT, (unsigned long long)nr);
+  if (lane == 0 && nr) atomicAdd(a.counters + CTR_REINJECT, (unsigned long long)nr);
+  if (kInstr) {
+    const unsigned nc = __reduce_add_sync(kFullMask, L.ncross);
+    const unsigned np = __reduce_add_sync(kFullMask, L.nprobe);
+    if (lane == 0) {
+      if (nc) atomicAdd(a.counters + CTR_CROSS, (unsigned long long)nc);
+      if (np) atomicAdd(a.counters + CTR_PROBE, (unsigned long long)np);
+    }
   }
 }
 
-// partial[s][j][c] = sum over the j-th slice of queue positions of stage[c][s][q] (c = 3: events), thread-strided then
-// a shared-memory tree: the order is fixed by (P, kStageSplits) alone.
+// file every exciton under its activity class (first launch after creation or after an upload of the population)
+__global__ void __launch_bounds__(256) classify_kernel(const Tables T, const int32_t* site, int64_t P, double dt, ClassLists q) {
+  const int64_t  e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int      lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const bool     mine = e < P;
+  const int      cls = mine ? activity_class(load_hop(T.site + site[e]).total * dt) : 0;
+  file_excitons(q, mine, cls, (uint32_t)e, lane, lt_mask);
+}
+
+// partial[s][j][c] = sum over the j-th slice of excitons of the (step, exciton) records, thread-strided then a
+// shared-memory tree: the order is fixed by (P, kStageSplits) alone.
 constexpr int kStageSplits = 16;
-__global__ void __launch_bounds__(256) reduce_stage_kernel(const double* stage, const uint32_t* stage_ev, int64_t P, int nsteps,
-                                                           double* partial) {
+__global__ void __launch_bounds__(256) reduce_stage_kernel(const StageRec* stage, int64_t P, int nsteps, double* partial) {
   __shared__ double sh[256][4];
   const int         s = blockIdx.x, j = blockIdx.y;
   const int64_t     len = (P + kStageSplits - 1) / kStageSplits;
   const int64_t     q0 = (int64_t)j * len, q1 = (q0 + len < P) ? q0 + len : P;
-  const size_t      plane = (size_t)nsteps * (size_t)P;
-  const size_t      row = (size_t)s * (size_t)P;
+  const double2*    row = reinterpret_cast<const double2*>(stage + (size_t)s * (size_t)P);
   double            v[4] = {0, 0, 0, 0};
   for (int64_t q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-    v[0] += __ldcs(stage + row + q);
-    v[1] += __ldcs(stage + plane + row + q);
-    v[2] += __ldcs(stage + 2 * plane + row + q);
-    v[3] += (double)__ldcs(stage_ev + row + q);
+    const double2 a = __ldcs(row + 2 * q), b = __ldcs(row + 2 * q + 1);
+    v[0] += a.x;
+    v[1] += a.y;
+    v[2] += b.x;
+    v[3] += b.y;
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) sh[threadIdx.x][c] = v[c];
