@@ -143,8 +143,8 @@ struct cntmc_handle {
   // device tables
   DevBuf<SiteRec> d_site;
   DevBuf<PosRec>  d_pos;
-  DevBuf<double>  d_cum;
-  DevBuf<int32_t> d_nbr, d_inject, d_c1, d_c2;
+  DevBuf<RowEntry> d_row;
+  DevBuf<int32_t>  d_inject, d_c1, d_c2;
   DevBuf<double>  d_theta, d_z, d_a1, d_a2, d_rates;
   Tables          T{};
 
@@ -360,11 +360,9 @@ void common_init(cntmc_t* h) {
   const uint64_t nnz = h->row_ptr[(size_t)N];
   if (nnz >= (1ull << 32)) throw std::invalid_argument("neighbour table has >= 2^32 entries; not supported by this build");
   d_row_begin.upload(h->row_ptr, st);
-  h->d_cum.alloc((size_t)nnz);
-  h->d_nbr.alloc((size_t)nnz);
+  h->d_row.alloc((size_t)nnz);
   a.row_begin = d_row_begin.p;
-  a.nbr = h->d_nbr.p;
-  a.cum = h->d_cum.p;
+  a.row = h->d_row.p;
   csr_rows_kernel<true><<<grid, block, 0, st>>>(a);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(h->ev1, st));
@@ -390,8 +388,7 @@ void common_init(cntmc_t* h) {
 
   h->T.site = h->d_site.p;
   h->T.pos = h->d_pos.p;
-  h->T.cum = h->d_cum.p;
-  h->T.nbr = h->d_nbr.p;
+  h->T.row = h->d_row.p;
   h->T.velocity = h->prm.velocity;
   h->time = 0;
   h->hops = h->reinjections = 0;
@@ -1066,9 +1063,15 @@ int cntmc_get_csr(const cntmc_t* h, int64_t* row_ptr, int32_t* nbr, double* cum)
     const size_t nnz = (size_t)h->row_ptr.back();
     if (row_ptr)
       for (size_t i = 0; i < h->row_ptr.size(); ++i) row_ptr[i] = (int64_t)h->row_ptr[i];
-    if (nbr) h->d_nbr.download(nbr, nnz, h->stream);
-    if (cum) h->d_cum.download(cum, nnz, h->stream);
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (nbr || cum) {
+      std::vector<RowEntry> rows(nnz);
+      h->d_row.download(rows.data(), nnz, h->stream);
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      for (size_t k = 0; k < nnz; ++k) {
+        if (nbr) nbr[k] = rows[k].nbr;
+        if (cum) cum[k] = rows[k].cum;
+      }
+    }
   });
 }
 int64_t cntmc_csr_midpoint_guards(const cntmc_t* h) { return h->midpoint_guards; }

@@ -380,14 +380,20 @@ std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vec
     pos[(size_t)i] = PosRec{x, y, z, 0.0};
     r.left = s.left[(size_t)i];
     r.right = s.right[(size_t)i];
-    r.q_left = r.q_right = 0.0;
+    // create_scatterers + trim_scats always produce symmetric links (monte_carlo.h:249-262, 730-772); anything else is a
+    // corrupted site list.
+    if ((r.left > -1 && s.right[(size_t)r.left] != (int32_t)i) || (r.right > -1 && s.left[(size_t)r.right] != (int32_t)i))
+      throw std::invalid_argument("chain links of the site list are not symmetric");
+    if (r.left > -1 && r.left == r.right) throw std::invalid_argument("a site is linked to the same neighbour on both sides");
+    r.q_right = r.q_left = 0.0;
     if (r.left > -1)
       r.q_left = segment_time(x, y, z, s.pos[0][(size_t)r.left], s.pos[1][(size_t)r.left], s.pos[2][(size_t)r.left], velocity);
     if (r.right > -1)
       r.q_right = segment_time(x, y, z, s.pos[0][(size_t)r.right], s.pos[1][(size_t)r.right], s.pos[2][(size_t)r.right], velocity);
     r.total = r.inv_total = 0.0;
     r.row_begin = r.row_len = 0;
-    r.guide[0] = r.guide[1] = r.guide[2] = r.guide[3] = 0;
+    for (int k = 0; k < 8; ++k) r.guide[k] = 0;
+    r.spare = 0.0;
   }
   return rec;
 }

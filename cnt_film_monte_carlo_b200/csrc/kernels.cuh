@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
       }
       if (have && (is_event ? runE : runS)) {
         const double t = is_event ? L.ff : dt_rem;
-        const Leg    leg = fly(L, a.T, t);
+        const Leg    leg = fly(L, a.T, t, !is_event);
         if (is_event) {
           dt_rem -= t;  // particle.cpp:63
           after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u);
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
           materialize(L, a.T);
           L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
           store_lane(L, a.S, (int64_t)e);
-          cls = activity_class(load_hop(a.T.site + L.site).total * a.dt);
+          cls = activity_class(hop_info(L, a.T).total * a.dt);
           if (kInstr && a.trace_counts) a.trace_counts[e] = trace_base + (int32_t)L.nevent;
           if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
           if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
@@ -553,8 +553,7 @@ struct CsrArgs {
   // outputs
   uint32_t*       deg;        // [N]      (count pass)
   const uint64_t* row_begin;  // [N+1]    (fill pass; exclusive scan of deg)
-  int32_t*        nbr;
-  double*         cum;
+  RowEntry*       row;        // [nnz]
   SiteRec*        site;       // rate fields of every record: total, 1/total, CSR row
   int32_t*        flags;
   unsigned long long* counters;
@@ -586,8 +585,11 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
           if (kFill) {
             const double rate = pair_rate(s1, s2, a.R, &guard);
             acc = (d == 0) ? rate : acc + rate;  // scatterer.cpp:78-80, sequential
-            a.nbr[base + d] = a.cell_sites[q];
-            a.cum[base + d] = acc;
+            RowEntry en;
+            en.cum = acc;
+            en.nbr = a.cell_sites[q];
+            en.pad = 0;
+            a.row[base + d] = en;
           }
           ++d;
         }
@@ -597,15 +599,16 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
   } else {
     a.site[i].total = acc;                  // scatterer.h:91  _max_rate = neighbors.back().first
     a.site[i].inv_total = d ? 1. / acc : 0.0;  // scatterer.h:92
-    uint8_t g8[kGuideBuckets];
-    build_guide(a.cum + base, d, acc, g8);  // reads back this thread's own row
-    uint32_t g[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < kGuideBuckets; ++j) g[j >> 2] |= (uint32_t)g8[j] << ((j & 3) * 8);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) a.site[i].guide[j] = g[j];
     a.site[i].row_begin = (uint32_t)base;
     a.site[i].row_len = d;
+    uint8_t g8[kGuideBuckets];
+    struct CumView {
+      const RowEntry* r;
+      __device__ double operator[](uint32_t k) const { return r[k].cum; }
+    };
+    build_guide(CumView{a.row + base}, d, acc, g8);  // reads back this thread's own row
+#pragma unroll
+    for (int j = 0; j < kGuideBuckets; ++j) a.site[i].guide[j] = g8[j];
     if (d == 0) atomicOr(a.flags + FLAG_EMPTY_ROW, 1);
     if (guard) atomicAdd(a.counters + CTR_GUARD, 1ULL);
   }

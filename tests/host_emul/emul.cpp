@@ -25,6 +25,7 @@ struct Emul {
   std::vector<PosRec>  pos;
   std::vector<double>  cum;
   std::vector<int32_t> nbr;
+  std::vector<RowEntry> row;
   std::vector<int64_t> row_ptr;
   Tables               T;
   std::vector<Lane>    lanes;
@@ -119,8 +120,9 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
     }
     e->T.site = e->site.data();
     e->T.pos = e->pos.data();
-    e->T.cum = e->cum.data();
-    e->T.nbr = e->nbr.data();
+    e->row.resize(e->cum.size());
+    for (size_t k = 0; k < e->cum.size(); ++k) e->row[k] = RowEntry{e->cum[k], e->nbr[k], 0};
+    e->T.row = e->row.data();
     e->T.inject = e->inj.sites.data();
     e->T.n_inject = (int32_t)e->inj.sites.size();
     for (int c = 0; c < 3; ++c) {
@@ -262,22 +264,29 @@ void emul_trace(Emul* e, int32_t* flat) {
     for (int32_t s : v) flat[k++] = s;
 }
 int64_t emul_select(const double* cum, int64_t d, double dice) { return (int64_t)select_entry(cum, 0u, (uint32_t)d - 1u, dice); }
+// the engine's own search over interleaved entries (nbr[k] = k so that the destination is the index)
+static int64_t select_via_entries(const double* cum, int64_t d, uint32_t lo, uint32_t hi, double dice) {
+  std::vector<RowEntry> row((size_t)d);
+  for (int64_t k = 0; k < d; ++k) row[(size_t)k] = RowEntry{cum[k], (int32_t)k, 0};
+  return select_dest(row.data(), lo, hi, dice);
+}
 // guided search exactly as after_flight_scatter performs it for draw r
 int64_t emul_select_guided(const double* cum, int64_t d, int32_t r) {
   const double total = cum[d - 1];
   uint8_t      g8[kGuideBuckets];
   build_guide(cum, (uint32_t)d, total, g8);
-  uint32_t g[4];
+  uint32_t g[2];
   memcpy(g, g8, sizeof(g));
   const double dice = total * (double)r / kRandMax;
   uint32_t     lo = 0, hi = (uint32_t)d - 1;
   if ((uint32_t)d <= kGuideMaxRow) {
     const uint32_t j = (uint32_t)r >> kGuideShift;
-    lo = guide_byte(g, j);
-    if (j + 1 < (uint32_t)kGuideBuckets) hi = guide_byte(g, j + 1);
+    lo = guide_byte(g[0], g[1], j);
+    if (j + 1 < (uint32_t)kGuideBuckets) hi = guide_byte(g[0], g[1], j + 1);
   }
-  return (int64_t)select_entry(cum, lo, hi, dice);
+  return select_via_entries(cum, d, lo, hi, dice);
 }
+int64_t emul_select_full(const double* cum, int64_t d, double dice) { return select_via_entries(cum, d, 0u, (uint32_t)d - 1u, dice); }
 void emul_philox2x32(uint32_t c0, uint32_t c1, uint32_t k, uint32_t* out) { philox2x32_10(c0, c1, k, out); }
 }  // extern "C"
 

@@ -79,13 +79,17 @@ def test_philox_matches_oracle_with_site_sequences(golden):
 
 
 def test_select_entry_equals_reference_loop():
+    import ctypes
     e = Emul(base_mc())
+    e.L.emul_select_full.restype = ctypes.c_int64
+    e.L.emul_select_full.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double]
     rng = np.random.default_rng(11)
     for _ in range(3000):
         d = int(rng.integers(1, 120))
         c = np.cumsum(rng.random(d) * (rng.random(d) > 0.25))
         for dice in (0.0, c[-1], c[-1] * rng.random(), float(rng.choice(c)), np.nextafter(float(rng.choice(c)), 0)):
             assert e.select(c, dice) == T1m.select(c, dice)
+            assert e.L.emul_select_full(c.ctypes.data, d, ctypes.c_double(dice)) == T1m.select(c, dice)  # the engine's entry search
 
 
 def test_guided_search_equals_reference_loop_for_every_bucket():
