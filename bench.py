@@ -217,8 +217,7 @@ def run_ours(args, rank, world, local_rank):
     pos, ori = film.film(**film.CONFIG_FILMS["C2"])
     eng = Engine(mc_block(P), device=local_rank, stream=stream.cuda_stream)
     eng.set_mesh(pos, ori)
-    for k, v in (("chunk_steps", args.chunk), ("hot_pct", args.hot_pct), ("occupancy", args.occupancy), ("park_min", args.park_min),
-                 ("park_wait", args.park_wait)):
+    for k, v in (("chunk_steps", args.chunk), ("hot_pct", args.hot_pct), ("occupancy", args.occupancy)):
         eng.set_option(k, v)
     eng.kubo_init()
     eng.kubo_create_particles(P, seed=1, first_global_id=rank * P)
@@ -363,9 +362,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--excitons", type=int, default=1_000_000, help="excitons per GPU")
     ap.add_argument("--intervals", type=int, default=100, help="sampling intervals (dt = 1e-13 s) per bench step")
-    ap.add_argument("--chunk", type=int, default=32, help="time steps per kernel launch")
-    ap.add_argument("--park-min", type=int, default=8)
-    ap.add_argument("--park-wait", type=int, default=4)
+    ap.add_argument("--chunk", type=int, default=64, help="time steps per kernel launch")
     ap.add_argument("--hot-pct", type=int, default=30, help="share of blocks serving the most active excitons first")
     ap.add_argument("--occupancy", type=int, default=5, help="resident 128-thread blocks per SM of the hop kernel (4, 5, 6, 8)")
     ap.add_argument("--e2e-steps", type=int, default=5)

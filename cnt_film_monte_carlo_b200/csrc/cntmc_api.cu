@@ -179,11 +179,9 @@ struct cntmc_handle {
   int64_t     last_launches = 0;
 
   // tuning
-  int64_t opt_chunk = 8;      // time steps per launch
+  int64_t opt_chunk = 64;     // time steps per launch
   int64_t opt_sort = 1;       // (kept for compatibility; activity classes replaced the sort)
   int64_t opt_hot_pct = 30;   // share of the blocks that serve the most active classes first
-  int64_t opt_park_min = 8;   // lanes that must want the warp's minority operation before it runs ...
-  int64_t opt_park_wait = 4;  // ... unless it has been waiting this many iterations
   int64_t opt_block = 128;  // threads per block of the hop kernel
   int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
   int64_t opt_stage_mb = 4096;  // cap on the (step, exciton) staging buffer; shortens the launches if needed
@@ -507,8 +505,6 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     a.draws = h->draws;
     a.q = lists(h->cur_list);
     a.hot_blocks = (int32_t)((int64_t)grid * h->opt_hot_pct / 100);
-    a.park_min = (int32_t)h->opt_park_min;
-    a.park_wait = (int32_t)h->opt_park_wait;
     a.P = h->P;
     a.dt = dt;
     a.nsteps = n;
@@ -1138,12 +1134,6 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "hot_pct") {
       require(value >= 0 && value <= 100, "hot_pct must be in [0, 100]");
       h->opt_hot_pct = value;
-    } else if (k == "park_min") {
-      require(value >= 1 && value <= 32, "park_min must be in [1, 32]");
-      h->opt_park_min = value;
-    } else if (k == "park_wait") {
-      require(value >= 0 && value <= 1000, "park_wait must be in [0, 1000]");
-      h->opt_park_wait = value;
     } else if (k == "occupancy") {
       require(value >= 4 && value <= 8, "occupancy must be 4 to 8 blocks per SM");
       h->opt_occupancy = value;
@@ -1166,8 +1156,6 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "block") return h->opt_block;
   if (k == "occupancy") return h->opt_occupancy;
   if (k == "hot_pct") return h->opt_hot_pct;
-  if (k == "park_min") return h->opt_park_min;
-  if (k == "park_wait") return h->opt_park_wait;
   if (k == "stage_mb") return h->opt_stage_mb;
   return -1;
 }

@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(256) create_excitons_kernel(const CreateArgs a
 // Activity classes.  Exciton activity is extremely skewed (on the C2 film the median exciton scatters twice in 64 steps,
 // the 99th percentile 1400 times: a few excitons sit in traps between closely crossing tubes) and it is predictable from
 // the state: Gamma(site) * dt = expected events per step if the exciton stays where it is.  When a lane stores an
-// exciton it files it under one of four classes; the next launch hands classes out from the hot end to "hot" blocks
-// and from the cold end to "cold" blocks, so that warps mostly hold excitons that run the same branch of the loop.
+// exciton it files it under one of four classes; in the next launch "hot" blocks serve the two active classes and
+// "cold" blocks the two quiet ones, so that warps mostly hold excitons that run the same branch of the loop.
 constexpr int kClasses = 4;
 __device__ __forceinline__ int activity_class(double expected_events_per_step) {
   return expected_events_per_step >= 8.0 ? 3 : expected_events_per_step >= 1.0 ? 2 : expected_events_per_step >= 0.125 ? 1 : 0;
@@ -175,7 +175,6 @@ struct KuboArgs {
   DrawConfig          draws;
   ClassLists          q;
   int32_t             hot_blocks;  // blocks [0, hot_blocks) serve the active classes first
-  int32_t             park_min, park_wait;  // see the loop of kubo_kernel
   int64_t             P;
   double              dt;
   int32_t             nsteps;
@@ -241,47 +240,35 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
       e = (uint32_t)e64;
       start();
     }
-    int waited = 0;
     while (__any_sync(kFullMask, have)) {
       bool finished = false;
-      // The next operation of a lane is known before it starts: a scattering event if the free flight ends inside the
-      // step, the end of the step otherwise.  The two kinds run different code, so the kind that is in the minority of
-      // this warp is parked until enough lanes want it (or it has waited park_wait iterations, or nothing else can
-      // run); the majority kind of the warp's role runs every iteration.
-      const bool     is_event = have && (L.ff <= dt_rem);  // particle.cpp:62
-      const unsigned mE = __ballot_sync(kFullMask, is_event), mS = __ballot_sync(kFullMask, have && !is_event);
-      const int      nE = __popc(mE), nS = __popc(mS);
-      bool           runE, runS;
-      if (role) {
-        runE = nE > 0;
-        runS = nS > 0 && (nS >= a.park_min || nE == 0 || waited >= a.park_wait);
-        waited = (nS > 0 && !runS) ? waited + 1 : 0;
-      } else {
-        runS = nS > 0;
-        runE = nE > 0 && (nE >= a.park_min || nS == 0 || waited >= a.park_wait);
-        waited = (nE > 0 && !runE) ? waited + 1 : 0;
+      // One iteration = up to two operations per lane: first the end of a time step for the lanes whose free flight
+      // outlasts the step, then a scattering event for the lanes whose flight ends inside the (possibly new) step.
+      // The warp pays the latency of both code paths anyway whenever both kinds are present, so a lane that ends a
+      // step and scatters right away gets both done in the same pass.
+      if (have && !(L.ff <= dt_rem)) {  // particle.cpp:62 false: the flight outlasts the step
+        const double t = dt_rem;
+        const Leg    leg = fly(L, a.T, t, true);
+        L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
+        after_flight_step_end(L, a.T, D, leg, t, s_old[0][tid], s_old[1][tid], s_old[2][tid]);
+        // streaming stores: written once, read once by the reduction, must not evict the tables from L2
+        double2* rec = reinterpret_cast<double2*>(a.stage + ((size_t)step * (size_t)a.P + (size_t)e));
+        __stcs(rec, make_double2(L.dx * L.dx, L.dy * L.dy));  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
+        __stcs(rec + 1, make_double2(L.dz * L.dz, (double)(L.nevent - ev0)));
+        s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
+        s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;
+        ++step;
+        dt_rem = a.dt;
+        ev0 = L.nevent;
+        finished = (step >= a.nsteps);
       }
-      if (have && (is_event ? runE : runS)) {
-        const double t = is_event ? L.ff : dt_rem;
-        const Leg    leg = fly(L, a.T, t, !is_event);
-        if (is_event) {
-          dt_rem -= t;  // particle.cpp:63
-          after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u);
-        } else {
-          L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
-          after_flight_step_end(L, a.T, D, leg, t, s_old[0][tid], s_old[1][tid], s_old[2][tid]);
-          // streaming stores: written once, read once by the reduction, must not evict the tables from L2
-          double2* rec = reinterpret_cast<double2*>(a.stage + ((size_t)step * (size_t)a.P + (size_t)e));
-          __stcs(rec, make_double2(L.dx * L.dx, L.dy * L.dy));  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
-          __stcs(rec + 1, make_double2(L.dz * L.dz, (double)(L.nevent - ev0)));
-          s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
-          s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;
-          ++step;
-          dt_rem = a.dt;
-          ev0 = L.nevent;
-        }
-        finished = (step >= a.nsteps) || L.stuck;
+      if (have && !finished && (L.ff <= dt_rem)) {
+        const double t = L.ff;
+        const Leg    leg = fly(L, a.T, t, false);
+        dt_rem -= t;  // particle.cpp:63
+        after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u);
       }
+      finished = have && (finished || L.stuck);
       if (__any_sync(kFullMask, finished)) {
         int cls = 0;
         if (finished) {

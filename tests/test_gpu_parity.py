@@ -189,3 +189,32 @@ def test_isolated_site_is_an_error_not_garbage():
     with pytest.raises(CntmcError) as ei:
         e.kubo_init()
     assert ei.value.code == -3 and "no neighbour" in str(ei.value)
+
+
+def test_dense_film_long_rows_against_oracle():
+    """BASELINE config 4's density at 1/50 of its size: 2 nm segmentation, rows of several hundred entries (beyond the
+    255-entry search guide), L2-spilling table.  Sampled rows and a short run must equal the oracle."""
+    pos, ori = film.film(NT=400, NP=250, a=2.0, LX=283.0, LY=100.0, seed=1234)
+    mc = base_mc()
+    e = Engine(mc)
+    e.set_mesh(pos, ori)
+    e.kubo_init()
+    t = T1m.T1()
+    t.kubo_init(mc, pos, ori)
+    rp, nbr, cum = e.csr()
+    deg = np.diff(rp)
+    assert deg.mean() > 150 and deg.max() > 255
+    rng = np.random.default_rng(0)
+    rows = np.concatenate([rng.integers(0, len(deg), 300), np.argsort(deg)[-20:], np.argsort(deg)[:20]])
+    for i in rows:
+        ids, c = t.row(int(i))
+        assert np.array_equal(ids, nbr[rp[i]:rp[i + 1]]) and np.array_equal(c, cum[rp[i]:rp[i + 1]]), i
+    st = t.sites()
+    assert np.array_equal(e.sites()["max_rate"], st["max_rate"])
+    t.set_memo(True)
+    t.draws_philox(2)
+    t.create_particles(3000)
+    t.kubo_step(1e-13, 12, want_msd=False)
+    e.kubo_create_particles(3000, seed=2)
+    e.kubo_step(1e-13, 12, want_msd=False)
+    assert np.array_equal(e.particles()["site"], t.particles()["site"]) and e.hops() == t.hops()
