@@ -327,11 +327,11 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref = CpuReference(args.cpu_excitons, os.cpu_count() or 1)
         h20, s20 = ref.step(20)
-        n_int = int(min(4000, max(20, 15.0 / max(s20 / 20, 1e-6))))   # about 15 s of CPU work
-        hops_c, sec_c = ref.step(n_int)
+        cpu_int = int(min(4000, max(20, 15.0 / max(s20 / 20, 1e-6))))   # about 15 s of CPU work
+        hops_c, sec_c = ref.step(cpu_int)
         cpu = {"value": hops_c / sec_c, "unit": "hops/s", "cores": ref.cores, "kind": ref.kind,
                "sample": "%d excitons x %d intervals of 1e-13 s on the C2 film (%.1f s), reference built against an Armadillo stand-in" % (
-                   args.cpu_excitons, n_int, sec_c)}
+                   args.cpu_excitons, cpu_int, sec_c)}
 
     if rank == 0:
         launches_per_step = eng.last_step_launches()

@@ -25,6 +25,8 @@ SIGNATURES = {
     "cntmc_set_rate_table": (C.c_int, [V, V, V, V, V, V, V]),
     "cntmc_get_rate_table_dims": (C.c_int, [V, V]),
     "cntmc_get_rate_table": (C.c_int, [V, V, V, V, V, V]),
+    "cntmc_save_rate_table": (C.c_int, [V, CP]),
+    "cntmc_load_rate_table": (C.c_int, [V, CP]),
     "cntmc_kubo_init": (C.c_int, [V]),
     "cntmc_kubo_create_particles": (C.c_int, [V, I64, U64, U64]),
     "cntmc_kubo_create_particles_replay": (C.c_int, [V, I64, V, V, V]),
@@ -46,6 +48,8 @@ SIGNATURES = {
     "cntmc_num_contact_sites": (C.c_int, [V, C.c_int, V]),
     "cntmc_get_contact_sites": (C.c_int, [V, C.c_int, V]),
     "cntmc_number_of_segments": (C.c_int, [V]),
+    "cntmc_get_scatterer_statistics": (C.c_int, [V, V]),
+    "cntmc_track_particle": (C.c_int, [V, D, U64, U64, I64, V, V, I64, V, V, V]),
     "cntmc_num_sites": (C.c_int, [V, V]),
     "cntmc_get_sites": (C.c_int, [V, V, V, V, V, V, V]),
     "cntmc_get_domain": (C.c_int, [V, V]),

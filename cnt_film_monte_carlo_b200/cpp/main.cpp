@@ -1,7 +1,7 @@
 // cpp/main.cpp -- command-line driver, the counterpart of the reference's src/main.cpp (same CLI: argv[1] = input JSON,
 // default "input.json"; same "exciton monte carlo" block; same output files), running on libcntmc.so.
 //
-//   cntmc_main [input.json] [--steps-per-call N] [--seed S] [--contacts ITERATIONS [--c1 N] [--c2 N]]
+//   cntmc_main [input.json] [--steps-per-call N] [--seed S] [--contacts ITERATIONS [--c1 N] [--c2 N] [--track N]]
 //
 // Without --contacts it runs the Green-Kubo loop of src/main.cpp:64-80.  With --contacts it runs ITERATIONS rounds of
 // the contact loop of src/main.cpp:98-106 (which the reference never reaches, and which never terminates there).
@@ -18,7 +18,7 @@ int main(int argc, char* argv[]) {
   std::cout << "\n***\nstart time:\n" << std::asctime(std::localtime(&start_time)) << "***\n\n";
 
   std::string filename = "input.json";
-  long long   steps_per_call = 1024, contact_iterations = -1, c1 = 1100, c2 = 0;
+  long long   steps_per_call = 1024, contact_iterations = -1, c1 = 1100, c2 = 0, n_track = 0, track_max_steps = 1 << 20;
   unsigned long long seed = 100;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -31,6 +31,8 @@ int main(int argc, char* argv[]) {
     else if (a == "--contacts") contact_iterations = value("--contacts");
     else if (a == "--c1") c1 = value("--c1");
     else if (a == "--c2") c2 = value("--c2");
+    else if (a == "--track") n_track = value("--track");
+    else if (a == "--track-max-steps") track_max_steps = value("--track-max-steps");
     else filename = a;
   }
 
@@ -70,6 +72,11 @@ int main(int argc, char* argv[]) {
     } else {
       sim.init(c1, c2);
       sim.save_json_properties();
+      if (n_track > 0) {  // src/main.cpp:88-92 (100 trajectories there)
+        std::cout << "saving particle trajectories ...";
+        for (int n = 0; n < (int)n_track; ++n) sim.track_particle(time_step, n, track_max_steps);
+        std::cout << "done!" << std::endl;
+      }
       std::cout << "\nrunning Monte Carlo:" << std::endl;
       for (long long it = 0; it < contact_iterations; ++it) {
         sim.step(time_step);

@@ -156,7 +156,39 @@ class monte_carlo {
     _last_pop.assign(_n_seg, 0);
     _last_curr.assign(_n_seg - 1, 0);
     std::cout << "number of segments: " << _n_seg << std::endl;
+    get_scatterer_statistics();
   }
+  // monte_carlo.h:691-719 (called from init(), :183)
+  void get_scatterer_statistics() {
+    std::vector<int64_t> pop(_n_seg, 0);
+    ok(cntmc_get_scatterer_statistics(_h, pop.data()));
+    int64_t n_sites = 0;
+    ok(cntmc_num_sites(_h, &n_sites));
+    const double ymin = _domain[1], ymax = _domain[4];
+    const double dy = (ymax - ymin) / double(_n_seg);
+    std::fstream f;
+    f.open((_output_directory / "scatterer_statistics.dat").string(), std::ios::out);
+    f << "position,distribution,population,density\n";
+    for (unsigned i = 0; i < _n_seg; ++i)
+      f << std::scientific << ymin + (double(i) + 0.5) * dy << "," << double(pop[i]) / double(n_sites) << "," << (long)pop[i] << ","
+        << double(pop[i]) / (_area[i] * dy) << "\n";
+    f.close();
+  }
+  // monte_carlo.h:786-818; the exciton's stream is (seed, fileNo); max_steps bounds the reference's unbounded loop
+  bool track_particle(double dt, int fileNo, int64_t max_steps = int64_t(1) << 20) {
+    std::vector<double> path((size_t)max_steps * 3);
+    int64_t             n = 0;
+    int32_t             reached = 0;
+    ok(cntmc_track_particle(_h, dt, _seed, (uint64_t)fileNo, 0, nullptr, nullptr, max_steps, path.data(), &n, &reached));
+    std::ofstream file((_output_directory / ("particle_path." + std::to_string(fileNo) + ".dat")).string(), std::ios::out);
+    file << std::scientific << std::showpos;
+    for (int64_t s = 0; s < n; ++s) file << "   " << path[3 * s] << " " << path[3 * s + 1] << " " << path[3 * s + 2] << "\n";
+    file << std::endl;
+    return reached != 0;
+  }
+  // scattering_struct::save into the output directory (monte_carlo.cpp:150) and its inverse
+  void save_scat_table() { ok(cntmc_save_rate_table(_h, _output_directory.string().c_str())); }
+  void load_scat_table(const std::string& dir) { ok(cntmc_load_rate_table(_h, dir.c_str())); }
   // monte_carlo.h:343-355; the engine performs step, the counting of save_metrics and repopulate_contacts in one call
   void step(double dt) { ok(cntmc_step(_h, dt, 1, _last_pop.data(), _last_curr.data())); }
   // monte_carlo.h:519-522

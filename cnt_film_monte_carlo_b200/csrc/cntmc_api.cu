@@ -683,6 +683,21 @@ int cntmc_get_rate_table(const cntmc_t* h, double* theta, double* z, double* a1,
   });
 }
 
+int cntmc_save_rate_table(const cntmc_t* h, const char* dir) {
+  return guarded(h, [&] {
+    require(dir != nullptr, "null directory");
+    require(!h->table.empty(), "no rate table yet");
+    save_rate_table(h->table, expand_home(dir));
+  });
+}
+int cntmc_load_rate_table(cntmc_t* h, const char* dir) {
+  return guarded(h, [&] {
+    require(dir != nullptr, "null directory");
+    require(!h->initialised, "cntmc_load_rate_table must precede initialisation");
+    h->table = load_rate_table(expand_home(dir));
+  });
+}
+
 int cntmc_kubo_init(cntmc_t* h) {
   return guarded(h, [&] {
     h->contact_mode = false;
@@ -990,6 +1005,67 @@ int cntmc_get_contact_sites(const cntmc_t* h, int which, int32_t* ids) {
   });
 }
 int cntmc_number_of_segments(const cntmc_t* h) { return h->prm.n_seg; }
+int cntmc_get_scatterer_statistics(const cntmc_t* h, int64_t* pop) {
+  return guarded(h, [&] {
+    require(h->initialised && h->contact_mode, "call cntmc_init first");
+    require(pop != nullptr, "null argument");
+    const auto c = slab_site_counts(h->sites, h->dom, h->n_seg);
+    std::copy(c.begin(), c.end(), pop);
+  });
+}
+
+int cntmc_track_particle(cntmc_t* h, double dt, uint64_t seed, uint64_t global_id, int64_t n_replay,
+                         const int32_t* replay_draws, const double* replay_logs, int64_t max_steps, double* path,
+                         int64_t* n_steps, int32_t* reached) {
+  return guarded(h, [&] {
+    require(h->initialised && h->contact_mode, "call cntmc_init first");
+    require(dt > 0 && max_steps > 0 && path && n_steps, "bad track_particle arguments");
+    require(n_replay == 0 || replay_draws != nullptr, "bad replay arguments");
+    if (h->c1_sites.empty()) throw StateError("the first contact holds no site (rand() % 0 in the reference, monte_carlo.h:477)");
+    use_device(h);
+    cudaStream_t     st = h->stream;
+    DevBuf<double>   d_path, d_logs;
+    DevBuf<int64_t>  d_out, d_off;
+    DevBuf<int32_t>  d_draws;
+    d_path.alloc((size_t)max_steps * 3);
+    d_out.alloc(3);
+    TrackArgs a{};
+    a.T = h->T;
+    a.draws.seed = seed;
+    a.draws.first_gid = global_id;
+    if (n_replay > 0) {
+      const int64_t off[2] = {0, n_replay};
+      d_off.upload(off, 2, st);
+      d_draws.upload(replay_draws, (size_t)n_replay, st);
+      if (replay_logs) d_logs.upload(replay_logs, (size_t)n_replay, st);
+      a.draws.replay_off = d_off.p;
+      a.draws.replay_draws = d_draws.p;
+      a.draws.replay_logs = replay_logs ? d_logs.p : nullptr;
+    }
+    a.c1_sites = h->d_c1.p;
+    a.n_c1 = (int32_t)h->c1_sites.size();
+    a.dt = dt;
+    const double ymin = h->dom.lo[1], ymax = h->dom.hi[1];
+    const double dy = (ymax - ymin) / double(h->n_seg);
+    a.y_stop = ymin + double(h->n_seg - 1) * dy;  // monte_carlo.h:809
+    a.max_steps = max_steps;
+    a.path = d_path.p;
+    a.n_out = d_out.p;
+    a.flags = h->d_flags.p;
+    if (n_replay > 0)
+      track_kernel<ReplayDraws><<<1, 32, 0, st>>>(a);
+    else
+      track_kernel<PhiloxDraws><<<1, 32, 0, st>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    int64_t out[3] = {0, 0, 0};
+    d_out.download(out, 3, st);
+    check_flags(h);  // synchronises
+    d_path.download(path, (size_t)out[0] * 3, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    *n_steps = out[0];
+    if (reached) *reached = (int32_t)out[1];
+  });
+}
 
 // ---- read-back -----------------------------------------------------------------------------------------------------------
 int cntmc_num_sites(const cntmc_t* h, int64_t* n) {

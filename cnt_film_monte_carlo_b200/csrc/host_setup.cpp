@@ -4,6 +4,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -179,6 +181,82 @@ void load_matrix(const std::string& path, int64_t& rows, int64_t& cols, std::vec
 }
 }  // namespace
 
+// ---- scat_table.*.dat -------------------------------------------------------------------------------------------------
+namespace {
+void write_column(const std::string& path, const std::vector<double>& v) {
+  std::ofstream f(path);
+  if (!f) throw std::invalid_argument("cannot write " + path);
+  char buf[40];
+  for (double x : v) {
+    snprintf(buf, sizeof buf, "%.17g\n", x);
+    f << buf;
+  }
+}
+std::vector<double> read_numbers(std::istream& f) {
+  std::vector<double> v;
+  std::string         tok;
+  while (f >> tok) {
+    char*        end = nullptr;
+    const double x = strtod(tok.c_str(), &end);
+    if (end == tok.c_str() || *end != '\0') throw std::invalid_argument("not a number: \"" + tok + "\"");
+    v.push_back(x);
+  }
+  return v;
+}
+std::vector<double> read_column(const std::string& path) {
+  std::ifstream f(path);
+  if (!f) throw std::invalid_argument("cannot open " + path);
+  return read_numbers(f);
+}
+}  // namespace
+
+void save_rate_table(const HostTable& t, const std::string& dir) {
+  const std::string base = dir + "/scat_table";
+  write_column(base + ".theta.dat", t.theta);
+  write_column(base + ".z_shift.dat", t.z);
+  write_column(base + ".axis_shift_1.dat", t.a1);
+  write_column(base + ".axis_shift_2.dat", t.a2);
+  std::ofstream f(base + ".rates.dat");
+  if (!f) throw std::invalid_argument("cannot write " + base + ".rates.dat");
+  f << "sizes:\n"
+    << "theta, z_shift, axis_shift_1, axis_shift_2\n"
+    << t.theta.size() << "," << t.z.size() << "," << t.a1.size() << "," << t.a2.size() << "\n\n";
+  char buf[40];
+  for (double x : t.rates) {
+    snprintf(buf, sizeof buf, "%.17g\n", x);
+    f << buf;
+  }
+}
+
+HostTable load_rate_table(const std::string& dir) {
+  const std::string base = dir + "/scat_table";
+  HostTable         t;
+  t.theta = read_column(base + ".theta.dat");
+  t.z = read_column(base + ".z_shift.dat");
+  t.a1 = read_column(base + ".axis_shift_1.dat");
+  t.a2 = read_column(base + ".axis_shift_2.dat");
+  std::ifstream f(base + ".rates.dat");
+  if (!f) throw std::invalid_argument("cannot open " + base + ".rates.dat");
+  std::string line;
+  std::getline(f, line);  // "sizes:"
+  std::getline(f, line);  // axis names
+  std::getline(f, line);  // n_theta,n_z,n_a1,n_a2
+  size_t dims[4] = {0, 0, 0, 0};
+  {
+    std::stringstream ss(line);
+    std::string       tok;
+    int               k = 0;
+    while (k < 4 && std::getline(ss, tok, ',')) dims[k++] = (size_t)strtoull(tok.c_str(), nullptr, 10);
+    if (k != 4) throw std::invalid_argument("scat_table.rates.dat: line 3 must hold the four table sizes");
+  }
+  if (dims[0] != t.theta.size() || dims[1] != t.z.size() || dims[2] != t.a1.size() || dims[3] != t.a2.size())
+    throw std::invalid_argument("scat_table.rates.dat: sizes do not match the axis files");
+  t.rates = read_numbers(f);
+  if (t.rates.size() != dims[0] * dims[1] * dims[2] * dims[3] || t.rates.empty())
+    throw std::invalid_argument("scat_table.rates.dat: wrong number of rates");
+  return t;
+}
+
 Mesh load_mesh(const std::string& dir) {
   Mesh        m;
   const char* ax[3] = {"x", "y", "z"};
@@ -348,6 +426,14 @@ std::vector<double> slab_areas(const Sites& s, const Domain& d, int n_seg) {
   std::vector<double> area((size_t)n_seg);
   for (int i = 0; i < n_seg; ++i) area[(size_t)i] = (zmax[(size_t)i] - zmin[(size_t)i]) * (xmax[(size_t)i] - xmin[(size_t)i]);
   return area;
+}
+
+std::vector<int64_t> slab_site_counts(const Sites& s, const Domain& d, int n_seg) {
+  const double         ymin = d.lo[1];
+  const double         dy = (d.hi[1] - ymin) / double(n_seg);
+  std::vector<int64_t> pop((size_t)n_seg, 0);
+  for (int64_t k = 0; k < s.N; ++k) pop[(size_t)(int(std::abs(s.pos[1][(size_t)k] - ymin) / dy) % n_seg)]++;
+  return pop;
 }
 
 std::vector<int32_t> contact_sites(const Sites& s, const Domain& d, int n_seg, int i) {

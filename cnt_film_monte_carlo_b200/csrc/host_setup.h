@@ -41,6 +41,13 @@ struct HostTable {
 };
 // monte_carlo::create_scattering_table for "forster" (gamma0 = 1e15) and "wong" (1e13)  (monte_carlo.cpp:24-61, 156-200)
 HostTable make_rate_table(const Params& p);
+// scattering_struct::save (scattering_struct.h:56-94): dir/scat_table.{theta,z_shift,axis_shift_1,axis_shift_2,rates}.dat.
+// Same files and layout (axes one value per line; rates.dat = "sizes:" header, the four sizes, a blank line, then the
+// rates theta-major); values are written with 17 significant digits so that a saved table loads back bit for bit
+// (the reference prints 6, Armadillo 4 for the axes).
+void save_rate_table(const HostTable& t, const std::string& dir);
+// the inverse (the reference only writes; visualization/monte_carlo_results.py:261-282 reads the files the same way)
+HostTable load_rate_table(const std::string& dir);
 
 struct Mesh {
   int64_t             n_tubes = 0, n_cols = 0;
@@ -81,6 +88,8 @@ Injection injection_region(const Sites& s, const Domain& d, int n_sections);
 std::vector<double>  slab_areas(const Sites& s, const Domain& d, int n_seg);              // monte_carlo.h:646-688
 std::vector<int32_t> contact_sites(const Sites& s, const Domain& d, int n_seg, int i);  // monte_carlo.h:494-516
 std::vector<int32_t> slab_sites_half_open(const Sites& s, const Domain& d, int n_seg, int i);  // monte_carlo.h:296-301
+// sites per slab as counted by monte_carlo::get_scatterer_statistics (monte_carlo.h:702-705): int(|y - ymin| / dy) % n_seg
+std::vector<int64_t> slab_site_counts(const Sites& s, const Domain& d, int n_seg);
 
 }  // namespace cntmc
 

@@ -526,6 +526,56 @@ __global__ void __launch_bounds__(256) gather_excitons_kernel(const ExcitonArray
   to.gid[i] = from.gid[s];
 }
 
+// ---- track_particle (monte_carlo.h:786-818) -------------------------------------------------------------------------------
+// One exciton born on the first contact (repopulate with n_particle = 1, monte_carlo.h:797-799) is stepped until it
+// enters the last slab; its position after every step is the row the reference writes to particle_path.N.dat.  A
+// diagnostic: one thread, bounded by max_steps (the reference's loop is unbounded).
+struct TrackArgs {
+  Tables         T;
+  DrawConfig     draws;  // Philox: (seed, first_gid) is the stream; replay: draws [replay_off[0], replay_off[1])
+  const int32_t* c1_sites;
+  int32_t        n_c1;
+  double         dt, y_stop;
+  int64_t        max_steps;
+  double*        path;   // [max_steps][3]
+  int64_t*       n_out;  // steps written, reached (0/1), events
+  int32_t*       flags;
+};
+template <typename Draws>
+__device__ __forceinline__ void init_track_draws(Draws& D, const DrawConfig& dc);
+template <>
+__device__ __forceinline__ void init_track_draws<PhiloxDraws>(PhiloxDraws& D, const DrawConfig& dc) {
+  D.init(dc.seed, dc.first_gid);
+}
+template <>
+__device__ __forceinline__ void init_track_draws<ReplayDraws>(ReplayDraws& D, const DrawConfig& dc) {
+  D.init(dc.replay_draws, dc.replay_logs, dc.replay_off[0], dc.replay_off[1]);
+}
+template <typename Draws>
+__global__ void track_kernel(const TrackArgs a) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Lane  L{};
+  Draws D{};
+  init_track_draws(D, a.draws);
+  create_exciton(L, a.T, D, a.c1_sites, a.n_c1);
+  int64_t n = 0;
+  while (L.py < a.y_stop && n < a.max_steps && !L.stuck && !D.exhausted()) {  // monte_carlo.h:811
+    Cursor c{};
+    begin_step(c, L, a.dt);
+    while (!advance_contact(L, a.T, D, c) && !L.stuck) {
+    }
+    a.path[3 * n + 0] = L.px;
+    a.path[3 * n + 1] = L.py;
+    a.path[3 * n + 2] = L.pz;
+    ++n;
+  }
+  a.n_out[0] = n;
+  a.n_out[1] = (L.py < a.y_stop) ? 0 : 1;
+  a.n_out[2] = (int64_t)L.nevent;
+  if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
+  if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
+}
+
 // ---- K1: neighbour table ---------------------------------------------------------------------------------------------------
 struct CsrArgs {
   const SiteGeom* geom;         // [N] site order

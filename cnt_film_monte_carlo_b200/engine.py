@@ -76,6 +76,13 @@ class Engine:
         self._ck(self.L.cntmc_get_rate_table(self.h, _p(th), _p(z), _p(a1), _p(a2), _p(rates)))
         return dict(theta=th, z=z, a1=a1, a2=a2, rates=rates)
 
+    def save_rate_table(self, directory: str):
+        """scattering_struct::save (scattering_struct.h:56-94): scat_table.*.dat"""
+        self._ck(self.L.cntmc_save_rate_table(self.h, directory.encode()))
+
+    def load_rate_table(self, directory: str):
+        self._ck(self.L.cntmc_load_rate_table(self.h, directory.encode()))
+
     def set_option(self, name: str, value: int):
         self._ck(self.L.cntmc_set_option(self.h, name.encode(), int(value)))
 
@@ -175,6 +182,27 @@ class Engine:
         a = np.empty(self.number_of_segments())
         self._ck(self.L.cntmc_get_area(self.h, _p(a)))
         return a
+
+    def scatterer_statistics(self):
+        """monte_carlo::get_scatterer_statistics (monte_carlo.h:691-719): sites per slab"""
+        pop = np.empty(self.number_of_segments(), np.int64)
+        self._ck(self.L.cntmc_get_scatterer_statistics(self.h, _p(pop)))
+        return pop
+
+    def track_particle(self, dt: float, seed: int = 1, global_id: int = 0, max_steps: int = 1 << 20, replay_draws=None,
+                       replay_logs=None):
+        """monte_carlo::track_particle (monte_carlo.h:786-818): (path [n][3], reached)"""
+        path = np.empty((max_steps, 3))
+        n, reached = C.c_int64(), C.c_int32()
+        if replay_draws is not None:
+            dr = np.ascontiguousarray(replay_draws, np.int32)
+            lg = None if replay_logs is None else np.ascontiguousarray(replay_logs, np.float64)
+            self._ck(self.L.cntmc_track_particle(self.h, dt, 0, 0, len(dr), _p(dr), None if lg is None else _p(lg), max_steps,
+                                                 _p(path), C.byref(n), C.byref(reached)))
+        else:
+            self._ck(self.L.cntmc_track_particle(self.h, dt, seed, global_id, 0, None, None, max_steps, _p(path), C.byref(n),
+                                                 C.byref(reached)))
+        return path[:n.value].copy(), bool(reached.value)
 
     def contact_sites(self, which: int):
         n = C.c_int64()

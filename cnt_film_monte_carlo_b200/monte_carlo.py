@@ -179,6 +179,32 @@ class monte_carlo:
         self._domain = self._engine.domain()
         self._say("number of segments: %d" % self._n_seg)
         self._say("total number of scatterers: %d" % self._engine.num_sites())
+        self.get_scatterer_statistics()
+
+    def get_scatterer_statistics(self) -> None:
+        """monte_carlo.h:691-719: scatterer_statistics.dat (called from init(), :183)."""
+        ymin, ymax = self._domain[1], self._domain[4]
+        dy = (ymax - ymin) / self._n_seg
+        pop = self._engine.scatterer_statistics()
+        total = self._engine.num_sites()
+        with open(os.path.join(self._output_directory, "scatterer_statistics.dat"), "w") as f:
+            f.write("position,distribution,population,density\n")
+            for i, (n, a) in enumerate(zip(pop, self._area)):
+                f.write("%.6e,%.6e,%d,%.6e\n" % (ymin + (i + 0.5) * dy, float(n) / float(total), n, float(n) / (a * dy)))
+
+    def track_particle(self, dt: float, file_no: int, max_steps: int = 1 << 20) -> bool:
+        """monte_carlo.h:786-818: particle_path.<file_no>.dat; the exciton's stream is (seed, file_no).  Returns whether
+        the last slab was reached within max_steps (the reference's loop is unbounded)."""
+        path, reached = self._engine.track_particle(dt, seed=self._seed, global_id=file_no, max_steps=max_steps)
+        with open(os.path.join(self._output_directory, "particle_path.%d.dat" % file_no), "w") as f:
+            for r in path:
+                f.write("   %+.6e %+.6e %+.6e\n" % tuple(r))
+            f.write("\n")
+        return reached
+
+    def save_scat_table(self) -> None:
+        """scattering_struct::save (scattering_struct.h:56-94) into the output directory (monte_carlo.cpp:150)."""
+        self._engine.save_rate_table(self._output_directory)
 
     def step(self, dt: float) -> None:
         """monte_carlo.h:343-355 -- together with save_metrics/repopulate_contacts (the engine fuses the three)."""

@@ -63,6 +63,12 @@ int cntmc_get_rate_table_dims(const cntmc_t* h, int32_t dims[4]);
 int cntmc_get_rate_table(const cntmc_t* h, double* theta, double* z_shift, double* axis_shift_1, double* axis_shift_2,
                          double* rates);
 
+/* scattering_struct::save  scattering_struct.h:56-94: dir/scat_table.{theta,z_shift,axis_shift_1,axis_shift_2,rates}.dat
+ * (same files and layout; 17 significant digits so that a saved table loads back bit for bit), and the loader the
+ * reference lacks (it only writes the files; visualization/monte_carlo_results.py:261-282 reads them the same way). */
+int cntmc_save_rate_table(const cntmc_t* h, const char* dir);
+int cntmc_load_rate_table(cntmc_t* h, const char* dir);
+
 /* ---- Green-Kubo flavour ------------------------------------------------------------------------------------------- */
 
 /* monte_carlo::kubo_init  monte_carlo/monte_carlo.cpp:254-305: rate table (create_scattering_table :24-61 for
@@ -116,6 +122,16 @@ int cntmc_get_area(const cntmc_t* h, double* area /* [n_seg] */);               
 int cntmc_num_contact_sites(const cntmc_t* h, int which, int64_t* n);           /* monte_carlo::contact_scats :494-516 */
 int cntmc_get_contact_sites(const cntmc_t* h, int which, int32_t* ids);
 int cntmc_number_of_segments(const cntmc_t* h);
+/* monte_carlo::get_scatterer_statistics  monte_carlo.h:691-719: sites per slab, pop [n_seg] (the shim writes
+ * scatterer_statistics.dat from it) */
+int cntmc_get_scatterer_statistics(const cntmc_t* h, int64_t* pop);
+/* monte_carlo::track_particle  monte_carlo.h:786-818: one exciton born on the first contact is stepped until it enters
+ * the last slab (or max_steps, which the reference does not have); path [max_steps][3] receives its position after
+ * every step, *n_steps the rows written, *reached (may be NULL) whether the last slab was entered.  The exciton's
+ * draws come from the stream (seed, global_id), or from a recorded list when n_replay > 0 (replay_logs may be NULL). */
+int cntmc_track_particle(cntmc_t* h, double dt, uint64_t seed, uint64_t global_id, int64_t n_replay,
+                         const int32_t* replay_draws, const double* replay_logs, int64_t max_steps, double* path,
+                         int64_t* n_steps, int32_t* reached);
 
 /* ---- read-back (parity tests, checkpoints, output writers) ------------------------------------------------------------ */
 

@@ -959,6 +959,29 @@ void t1_contact_iteration(t1_sim* s, double dt, int64_t* pop, int64_t* curr) {
   repopulate(s, ymin + (double)(n - 1) * dy, ymax, s->c2_pop, s->c2, s->n_c2);
 }
 
+/* monte_carlo::track_particle (monte_carlo.h:786-818): one exciton created on the first contact by repopulate(...,1,...),
+ * stepped while pos.y < ymin + (n_seg-1)*dy; path receives the position after every step.  max_steps bounds the
+ * reference's unbounded loop.  Returns the number of rows; *reached tells whether the last slab was entered. */
+int64_t t1_track_particle(t1_sim* s, double dt, uint64_t gid, int64_t max_steps, double* path, int32_t* reached) {
+  int32_t*     tmp_ids = (int32_t*)malloc(ROW_CAP * sizeof(int32_t));
+  double*      tmp_cum = (double*)malloc(ROW_CAP * sizeof(double));
+  const double ymin = s->lo[1], ymax = s->hi[1];
+  const double dy = (ymax - ymin) / (double)s->n_seg;
+  const double y1 = ymin + (double)(s->n_seg - 1) * dy;
+  exciton_t    e;
+  make_exciton(s, &e, gid, s->c1, s->n_c1);
+  int64_t n = 0;
+  while (e.pos[1] < y1 && n < max_steps) {
+    particle_step(s, &e, dt, tmp_ids, tmp_cum);
+    for (int c = 0; c < 3; ++c) path[3 * n + c] = e.pos[c];
+    ++n;
+  }
+  if (reached) *reached = !(e.pos[1] < y1);
+  free(tmp_ids);
+  free(tmp_cum);
+  return n;
+}
+
 /* log(r / RAND_MAX) with the host libm, for every recorded draw: fed to the engine's replay mode so that free-flight
  * times are bit-identical to a glibc run (scatterer.h:79). */
 void t1_log_ratios(const int32_t* draws, int64_t n, double* out) {

@@ -86,6 +86,8 @@ void    t1_area(const t1_sim* s, double* area);
 int64_t t1_num_contact_sites(const t1_sim* s, int which);
 void    t1_contact_sites(const t1_sim* s, int which, int32_t* ids);
 void    t1_contact_iteration(t1_sim* s, double dt, int64_t* pop /* [n_seg] */, int64_t* curr /* [n_seg-1] */);
+int64_t t1_track_particle(t1_sim* s, double dt, uint64_t gid, int64_t max_steps, double* path /* [max_steps][3] */,
+                          int32_t* reached); /* monte_carlo.h:786-818 */
 
 #ifdef __cplusplus
 }

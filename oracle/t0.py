@@ -187,3 +187,9 @@ class T0:
 
     def contact_iteration(self, dt: float) -> None:
         self.L.t0_contact_iteration(dt)
+
+    def track_particle(self, dt: float, file_no: int, log_slot: int = 0) -> None:
+        """monte_carlo::track_particle (monte_carlo.h:786-818); writes particle_path.<file_no>.dat in the output directory."""
+        self.L.t0_track_particle.argtypes = [C.c_double, C.c_int, C.c_int64]
+        self.L.t0_track_particle.restype = None
+        self.L.t0_track_particle(dt, file_no, log_slot)

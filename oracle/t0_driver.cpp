@@ -375,4 +375,11 @@ void t0_contact_iteration(double dt) {
   g_sim->save_metrics(dt);
   g_sim->repopulate_contacts();
 }
+// monte_carlo::track_particle (monte_carlo.h:786-818), verbatim; every draw is attributed to exciton `log_slot`
+void t0_track_particle(double dt, int file_no, int64_t log_slot) {
+  cout_silencer quiet;
+  attribute_to(log_slot);
+  g_sim->track_particle(dt, file_no);
+  g_cur = -1;
+}
 }  // extern "C"

@@ -87,6 +87,7 @@ def _lib():
         "t1_num_contact_sites": (I64, [V, C.c_int]),
         "t1_contact_sites": (None, [V, C.c_int, V]),
         "t1_contact_iteration": (None, [V, D, V, V]),
+        "t1_track_particle": (I64, [V, D, C.c_uint64, I64, V, V]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -339,6 +340,14 @@ class T1:
         pop, cur = np.empty(self.n_seg, np.int64), np.empty(self.n_seg - 1, np.int64)
         self.L.t1_contact_iteration(self.h, dt, _p(pop), _p(cur))
         return pop, cur
+
+
+    def track_particle(self, dt: float, gid: int = 0, max_steps: int = 1 << 20):
+        """monte_carlo::track_particle (monte_carlo.h:786-818): (path [n][3], reached)"""
+        path = np.empty((max_steps, 3))
+        reached = C.c_int32()
+        n = self.L.t1_track_particle(self.h, dt, gid, max_steps, _p(path), C.byref(reached))
+        return path[:n].copy(), bool(reached.value)
 
 
 def load_mc_block(json_path: str) -> dict:

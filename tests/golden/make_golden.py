@@ -40,7 +40,7 @@ CASES = {
             "maximum time for kubo simulation [seconds]": 3e-12,
             "number of particles for kubo simulation": 50,
         },
-        seed=100, nsteps=300, contact_steps=80),
+        seed=100, nsteps=300, contact_steps=80, track_dt=2e-12),
     "wong_trimmed": dict(
         film=dict(NT=30, NP=40, a=4.0, LX=80.0, LY=50.0, seed=11),
         mc={
@@ -120,9 +120,15 @@ def make(name, case):
                 t.contact_iteration(dt)
                 npart.append(t.L.t0_num_particles())
             g["contact_num_particles"] = np.array(npart)
+            # monte_carlo::track_particle (monte_carlo.h:786-818) with its draws logged; writes particle_path.3.dat
+            t.L.t0_clear_draws()
+            t.log_draws(True)
+            t.track_particle(case["track_dt"], 3, 0)
+            _, tflat = t.draws(1)
+            g["track_dt"], g["track_draws"], g["track_logs"] = case["track_dt"], tflat, T1m.log_ratios(tflat)
             t.close()
             for name_, key in (("population_profile.dat", "contact_pop_file"), ("region_current.dat", "contact_curr_file"),
-                               ("scatterer_statistics.dat", "contact_stat_file")):
+                               ("scatterer_statistics.dat", "contact_stat_file"), ("particle_path.3.dat", "track_file")):
                 with open(os.path.join(tmp, "out_contacts", name_)) as f:
                     g[key] = np.frombuffer(f.read().encode(), dtype=np.uint8)
     mc_clean = dict(case["mc"])

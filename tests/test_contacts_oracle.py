@@ -51,3 +51,21 @@ def test_philox_contact_run_is_reproducible_and_conserves_excitons(golden_small)
         hist = [t.contact_iteration(DT) for _ in range(40)]
         runs.append((np.array([h[0] for h in hist]), np.array([h[1] for h in hist])))
     assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+
+
+def format_path(path):
+    """the rows monte_carlo::track_particle writes (monte_carlo.h:806-815): showpos, scientific, 6 digits"""
+    return "".join("   %+.6e %+.6e %+.6e\n" % tuple(r) for r in path) + "\n"
+
+
+def test_track_particle_reproduces_reference_file(golden_small):
+    g = golden_small
+    flat = g.z["track_draws"]
+    t = T1m.T1()
+    t.contacts_init(g.mc, g.pos_nm, g.orient)
+    t.draws_replay(np.array([0, len(flat)], np.int64), flat)
+    path, reached = t.track_particle(float(g.z["track_dt"]), gid=0)
+    assert reached and not t.replay_exhausted()
+    assert format_path(path) == bytes(g.z["track_file"]).decode()
+    extra, _ = t.track_particle(float(g.z["track_dt"]), gid=0, max_steps=len(path) - 1)
+    assert len(extra) == len(path) - 1 and np.array_equal(extra, path[:-1])

@@ -61,3 +61,62 @@ def test_larger_film_contacts():
     pop, cur = e.step(1e-13, 25)
     assert np.array_equal(pop, pop_t) and np.array_equal(cur, cur_t)
     assert e.number_of_particles() == t.L.t1_num_particles(t.h)
+
+
+def format_path(path):
+    """the rows monte_carlo::track_particle writes (monte_carlo.h:806-815): showpos, scientific, 6 digits"""
+    return "".join("   %+.6e %+.6e %+.6e\n" % tuple(r) for r in path) + "\n"
+
+
+def test_track_particle_replays_the_reference_trajectory(golden_small):
+    """monte_carlo::track_particle: with the reference's own draws the path file is reproduced byte for byte."""
+    g = golden_small
+    e = Engine(g.mc)
+    e.set_mesh(g.pos_nm, g.orient)
+    e.init(0, 0)
+    path, reached = e.track_particle(float(g.z["track_dt"]), replay_draws=g.z["track_draws"], replay_logs=g.z["track_logs"])
+    assert reached
+    assert format_path(path) == bytes(g.z["track_file"]).decode()
+    t = T1m.T1()
+    t.contacts_init(g.mc, g.pos_nm, g.orient)
+    t.draws_replay(np.array([0, len(g.z["track_draws"])], np.int64), g.z["track_draws"])
+    path_t, _ = t.track_particle(float(g.z["track_dt"]))
+    assert np.array_equal(path, path_t)               # bit for bit, not only to the 7 printed digits
+
+
+def test_track_particle_philox_matches_oracle(golden_small):
+    g = golden_small
+    e = Engine(g.mc)
+    e.set_mesh(g.pos_nm, g.orient)
+    e.init(0, 0)
+    t = T1m.T1()
+    t.draws_philox(21)
+    t.set_memo(True)
+    t.contacts_init(g.mc, g.pos_nm, g.orient, c1_pop=0, c2_pop=0)
+    for gid in (0, 5):
+        path, reached = e.track_particle(1e-12, seed=21, global_id=gid, max_steps=4000)
+        path_t, reached_t = t.track_particle(1e-12, gid=gid, max_steps=4000)
+        assert reached == reached_t and path.shape == path_t.shape and len(path) > 10
+        assert np.allclose(path, path_t, rtol=1e-9, atol=1e-18)
+    short, reached = e.track_particle(1e-12, seed=21, global_id=0, max_steps=7)     # the bound the reference lacks
+    assert len(short) == 7 and not reached
+    assert np.allclose(short, t.track_particle(1e-12, gid=0, max_steps=7)[0], rtol=1e-9, atol=1e-18)
+
+
+def test_mirror_writes_statistics_and_path_files(golden_small, tmp_path):
+    from cnt_film_monte_carlo_b200.monte_carlo import monte_carlo
+    g = golden_small
+    mesh, out = str(tmp_path / "mesh"), str(tmp_path / "out")
+    film.write_mesh(mesh, g.pos_nm, g.orient)
+    mc = dict(g.mc, **{"mesh input directory": mesh, "output directory": out})
+    sim = monte_carlo(mc, quiet=True)
+    sim.init()
+    with open(out + "/scatterer_statistics.dat") as f:
+        assert f.read() == bytes(g.z["contact_stat_file"]).decode()      # monte_carlo.h:691-719, the reference's own file
+    assert sim.track_particle(2e-12, 3, max_steps=100000)
+    with open(out + "/particle_path.3.dat") as f:
+        rows = [ln for ln in f.read().splitlines() if ln]
+    dom = sim._domain
+    y_last = float(rows[-1].split()[1])
+    assert y_last >= dom[1] + 0.9 * (dom[4] - dom[1]) and all(float(r.split()[1]) < dom[1] + 0.9 * (dom[4] - dom[1]) for r in rows[:-1])
+    sim.close()
