@@ -222,6 +222,8 @@ def run_ours(args, rank, world, local_rank):
     eng.set_mesh(pos, ori)
     for k, v in (("chunk_steps", args.chunk), ("hot_pct", args.hot_pct), ("occupancy", args.occupancy)):
         eng.set_option(k, v)
+    if args.stage_mb > 0:
+        eng.set_option("stage_mb", args.stage_mb)
     eng.kubo_init()
     eng.kubo_create_particles(P, seed=1, first_global_id=rank * P)
 
@@ -374,6 +376,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=64, help="time steps per kernel launch")
     ap.add_argument("--hot-pct", type=int, default=30, help="share of blocks serving the most active excitons first")
     ap.add_argument("--occupancy", type=int, default=5, help="resident 128-thread blocks per SM of the hop kernel (4, 5, 6, 8)")
+    ap.add_argument("--stage-mb", type=int, default=0, help="cap on the (step, exciton) staging buffer in MiB (0 = engine default)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-excitons", type=int, default=8000)
     ap.add_argument("--cpu-budget", type=float, default=100.0, help="seconds of CPU work for the whole --impl reference run")

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcntmc.so")
+LIB_PATH = os.environ.get("CNTMC_LIB") or os.path.join(HERE, "libcntmc.so")  # override: kernel experiments only
 
 V, I32, I64, U64, D, CP = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_char_p
 

@@ -184,7 +184,8 @@ struct cntmc_handle {
   int64_t opt_hot_pct = 30;   // share of the blocks that serve the most active classes first
   int64_t opt_block = 128;  // threads per block of the hop kernel
   int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
-  int64_t opt_stage_mb = 4096;  // cap on the (step, exciton) staging buffer; shortens the launches if needed
+  int64_t opt_stage_mb = 0;  // cap on the (step, exciton) staging buffer in MiB; shortens the launches if needed.
+                             // 0 = a third of the device memory that is free when the buffer is first sized
   int     sm_count = 0;
   int64_t opt_stats = 0;         // count cumulative-rate probes and chain crossings (roofline bookkeeping)
   int64_t opt_time_kernels = 0;  // CUDA events around every hop-kernel launch (bench.py's roofline figure)
@@ -462,6 +463,11 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   // time steps per launch: the option, capped so that the (step, exciton) staging buffer stays within its budget
+  if (h->opt_stage_mb <= 0) {
+    size_t free_b = 0, total_b = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    h->opt_stage_mb = std::max<int64_t>(256, (int64_t)((free_b + h->d_stage.n * sizeof(StageRec)) / 3) >> 20);
+  }
   const int64_t by_budget = std::max<int64_t>(1, (h->opt_stage_mb << 20) / ((int64_t)sizeof(StageRec) * h->P));
   const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({h->opt_chunk, by_budget, nsteps}));
   // persistent grid: as many 128-thread blocks as the SMs hold at the compiled occupancy, never more than needed
@@ -1214,7 +1220,7 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
       require(value >= 4 && value <= 8, "occupancy must be 4 to 8 blocks per SM");
       h->opt_occupancy = value;
     } else if (k == "stage_mb") {
-      require(value >= 1, "stage_mb must be positive");
+      require(value >= 0, "stage_mb must not be negative (0 = a third of the free device memory)");
       h->opt_stage_mb = value;
     } else if (k == "stats") {
       h->opt_stats = value ? 1 : 0;
