@@ -1189,6 +1189,8 @@ int cntmc_trace_enable(cntmc_t* h, int32_t cap) {
       h->d_trace_sites.alloc((size_t)h->P * cap);
       h->d_trace_counts.alloc((size_t)h->P);
       CUDA_CHECK(cudaMemsetAsync(h->d_trace_counts.p, 0, (size_t)h->P * sizeof(int32_t), h->stream));
+      // unused slots read back as -1 (cntmc_trace_get copies the whole [P][cap] array)
+      CUDA_CHECK(cudaMemsetAsync(h->d_trace_sites.p, 0xff, (size_t)h->P * cap * sizeof(int32_t), h->stream));
     }
   });
 }

@@ -598,6 +598,10 @@ struct CsrArgs {
 
 // Enumerate the candidates of site i in the reference's order: the 27-cell stencil with x outermost and z innermost
 // (monte_carlo.h:402-411), sites of a cell in ascending list order (monte_carlo.h:389-395).
+//
+// Only about one candidate in six lies inside the cutoff sphere, and the work per accepted pair (acos, four nearest-grid
+// searches) is ~15x the distance test.  The loop is therefore split in two: every lane first advances its own cursor
+// to its next accepted candidate (cheap, divergent), then the lanes of the warp evaluate their pairs together.
 template <bool kFill>
 __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -610,27 +614,44 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
   uint64_t base = 0;
   bool     guard = false;
   if (kFill) base = a.row_begin[i];
-  for (int ix = cx - 1; ix <= cx + 1; ++ix)
-    for (int iy = cy - 1; iy <= cy + 1; ++iy)
-      for (int iz = cz - 1; iz <= cz + 1; ++iz) {
-        if (!(ix > -1 && ix < a.nb[0] && iy > -1 && iy < a.nb[1] && iz > -1 && iz < a.nb[2])) continue;
-        const int64_t b = (int64_t)ix + (int64_t)iy * a.nb[0] + (int64_t)iz * a.nb[0] * a.nb[1];
-        const int64_t q1 = a.cell_start[b + 1];
-        for (int64_t q = a.cell_start[b]; q < q1; ++q) {
-          const SiteGeom s2 = a.cell_geom[q];
-          if (!within_cutoff(s1, s2, a.radius)) continue;
-          if (kFill) {
-            const double rate = pair_rate(s1, s2, a.R, &guard);
-            acc = (d == 0) ? rate : acc + rate;  // scatterer.cpp:78-80, sequential
-            RowEntry en;
-            en.cum = acc;
-            en.nbr = a.cell_sites[q];
-            en.pad = 0;
-            a.row[base + d] = en;
+  int      c = -1;  // ordinal of the current stencil cell: ix = cx-1 + c/9, iy = cy-1 + (c/3)%3, iz = cz-1 + c%3
+  int64_t  q = 0, q1 = 0;
+  for (;;) {
+    bool     found = false;
+    SiteGeom s2{};
+    int64_t  qf = 0;
+    while (!found) {
+      if (q >= q1) {  // next non-empty cell of the stencil, in the reference's order
+        bool more = false;
+        while (++c < 27) {
+          const int ix = cx - 1 + c / 9, iy = cy - 1 + (c / 3) % 3, iz = cz - 1 + c % 3;
+          if (!(ix > -1 && ix < a.nb[0] && iy > -1 && iy < a.nb[1] && iz > -1 && iz < a.nb[2])) continue;
+          const int64_t b = (int64_t)ix + (int64_t)iy * a.nb[0] + (int64_t)iz * a.nb[0] * a.nb[1];
+          q = a.cell_start[b];
+          q1 = a.cell_start[b + 1];
+          if (q < q1) {
+            more = true;
+            break;
           }
-          ++d;
         }
+        if (!more) break;
       }
+      s2 = a.cell_geom[q];
+      qf = q++;
+      found = within_cutoff(s1, s2, a.radius);
+    }
+    if (!found) break;
+    if (kFill) {
+      const double rate = pair_rate(s1, s2, a.R, &guard);
+      acc = (d == 0) ? rate : acc + rate;  // scatterer.cpp:78-80, sequential
+      RowEntry en;
+      en.cum = acc;
+      en.nbr = a.cell_sites[qf];
+      en.pad = 0;
+      a.row[base + d] = en;
+    }
+    ++d;
+  }
   if (!kFill) {
     a.deg[i] = d;
   } else {

@@ -1,0 +1,69 @@
+"""BASELINE config 2 at full size (1e5 sites, 1e6 excitons) through the C ABI: the oracle cannot run this in seconds,
+so the checks are size-independent properties of the path plus an oracle spot check on a sample of
+excitons (streams are keyed by global id, so any sub-population can be re-run alone)."""
+import numpy as np
+import pytest
+
+from cnt_film_monte_carlo_b200 import film
+from cnt_film_monte_carlo_b200.engine import Engine
+from oracle import t1 as T1m
+from conftest import base_mc
+
+pytestmark = pytest.mark.gpu
+
+P, DT, STEPS = 1_000_000, 1e-13, 48
+
+
+@pytest.fixture(scope="module")
+def c2():
+    pos, ori = film.film(**film.CONFIG_FILMS["C2"])
+    mc = base_mc(**{"number of particles for kubo simulation": P})
+    return mc, pos, ori
+
+
+def run(c2, opts, first=0, count=P, steps=(STEPS,), trace=0):
+    mc, pos, ori = c2
+    e = Engine(mc)
+    e.set_mesh(pos, ori)
+    for k, v in opts.items():
+        e.set_option(k, v)
+    e.kubo_init()
+    e.kubo_create_particles(count, seed=1, first_global_id=first)
+    p0 = e.particles()
+    msd = np.concatenate([e.kubo_step(DT, n) for n in steps])
+    return e, p0, e.particles(), msd
+
+
+def test_full_size_properties(c2):
+    e, p0, p1, msd = run(c2, dict(chunk_steps=64))
+    # every draw is accounted for: creation takes 3 (site, free flight, heading), an event 2, a re-injection 1
+    assert int(p1["ndraw"].astype(np.int64).sum()) == 3 * P + 2 * e.hops() + e.reinjections()
+    assert e.hops() > 20 * P * 0.5
+    # displacement telescopes for every exciton that was not re-injected (SURVEY.md §8c pin 7)
+    off = np.abs(p1["delta"] - (p1["pos"] - p0["pos"])).max(axis=0) > 1e-18
+    assert off.sum() <= e.reinjections()
+    # the ensemble rows are the mean of squares of what the excitons carry at the end
+    assert np.allclose(msd[-1], (p1["delta"] ** 2).mean(axis=1), rtol=1e-12, atol=0)
+    # early on the motion is ballistic along the tubes: the MSD grows at every step (later the excitons turn around at
+    # the tube ends -- 100 sites x 5 nm against 20 nm of flight per step -- and it may shrink again)
+    assert np.all(np.diff(msd.sum(axis=1)[:12]) > 0) and np.all(msd > 0)
+    # launch size, scheduling options and splitting the call change nothing, bit for bit
+    e2, _, q1, msd2 = run(c2, dict(chunk_steps=16, hot_pct=0, occupancy=6), steps=(5, STEPS - 5))
+    assert all(np.array_equal(p1[k], q1[k]) for k in p1)
+    assert np.array_equal(msd, msd2) and e2.hops() == e.hops()
+    # a shard of the population run alone follows the same trajectories (what multi-GPU sharding relies on)
+    first, count = 700_000, 4096
+    _, _, s1, _ = run(c2, dict(chunk_steps=7), first=first, count=count)
+    assert all(np.array_equal(s1[k], p1[k][..., first:first + count]) for k in s1)
+    # and the oracle agrees on that shard: same sites, same number of draws, positions within libm log's last ulp
+    mc, pos, ori = c2
+    t = T1m.T1()
+    t.draws_philox(1)
+    t.set_memo(True)
+    t.kubo_init(mc, pos, ori)
+    n_o = 256
+    t.create_particles(n_o, first_global_id=first)
+    t.kubo_step(DT, STEPS, want_msd=False)
+    pt = t.particles()
+    assert np.array_equal(pt["site"], s1["site"][:n_o]) and np.array_equal(pt["heading"].astype(np.uint8), s1["heading"][:n_o])
+    assert np.allclose(pt["pos"], s1["pos"][:, :n_o], rtol=1e-9, atol=1e-18) and np.allclose(pt["delta"], s1["delta"][:, :n_o], rtol=1e-9, atol=1e-18)
