@@ -444,9 +444,29 @@ void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st
 template <typename Draws>
 void launch_kubo(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) {
   // the instrumented variant (site traces, probe / crossing counters) runs only when somebody asked for its output
-  if (h->trace_cap > 0 || h->opt_stats)
+  if (h->trace_cap > 0 || h->opt_stats) {
+    // the residency counters describe the last instrumented launch only
+    CUDA_CHECK(cudaMemsetAsync(h->d_counters.p + CTR_WARP_NS, 0, (CTR_COUNT - CTR_WARP_NS) * sizeof(unsigned long long), st));
+    const char* dump = getenv("CNTMC_DEBUG_WARP_TIMES");  // diagnostics: per-warp timestamps of this launch -> file
+    if (dump && *dump) {
+      KuboArgs                   b = a;
+      DevBuf<unsigned long long> d_times;
+      const size_t               n = (size_t)grid * 4 * 4;
+      d_times.alloc(n);
+      CUDA_CHECK(cudaMemsetAsync(d_times.p, 0, n * sizeof(unsigned long long), st));
+      b.warp_times = d_times.p;
+      launch_kubo_i<Draws, true>(h, b, grid, st);
+      std::vector<unsigned long long> host(n);
+      d_times.download(host.data(), n, st);
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      if (FILE* f = fopen(dump, "wb")) {
+        fwrite(host.data(), sizeof(unsigned long long), n, f);
+        fclose(f);
+      }
+      return;
+    }
     launch_kubo_i<Draws, true>(h, a, grid, st);
-  else
+  } else
     launch_kubo_i<Draws, false>(h, a, grid, st);
 }
 
@@ -1241,6 +1261,15 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "occupancy") return h->opt_occupancy;
   if (k == "hot_pct") return h->opt_hot_pct;
   if (k == "stage_mb") return h->opt_stage_mb;
+  if (k.rfind("dbg_", 0) == 0) {  // raw device counters of the last instrumented hop-kernel launch (option "stats")
+    unsigned long long ctrs[CTR_COUNT];
+    if (!h->d_counters.p || cudaMemcpy(ctrs, h->d_counters.p, sizeof ctrs, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (k == "dbg_warp_ns") return (int64_t)ctrs[CTR_WARP_NS];
+    if (k == "dbg_span_ns") return (int64_t)(ctrs[CTR_T_LAST] - ~ctrs[CTR_T_FIRST_INV]);
+    if (k == "dbg_warps") return (int64_t)ctrs[CTR_WARPS];
+    if (k == "dbg_lane_busy") return (int64_t)ctrs[CTR_LANE_BUSY];
+    if (k == "dbg_lane_idle") return (int64_t)ctrs[CTR_LANE_IDLE];
+  }
   return -1;
 }
 double  cntmc_last_step_ms(const cntmc_t* h) { return h->last_ms; }

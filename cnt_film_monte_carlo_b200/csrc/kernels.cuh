@@ -80,7 +80,18 @@ __device__ __forceinline__ void init_draws<ReplayDraws>(ReplayDraws& D, const Dr
 }
 
 enum { FLAG_STUCK = 0, FLAG_REPLAY = 1, FLAG_EMPTY_ROW = 2, FLAG_COUNT = 4 };
-enum { CTR_REINJECT = 0, CTR_GUARD = 1, CTR_CROSS = 2, CTR_PROBE = 3, CTR_QUEUE = 4, CTR_EVENTS = 5, CTR_COUNT = 8 };
+enum {
+  CTR_REINJECT = 0, CTR_GUARD = 1, CTR_CROSS = 2, CTR_PROBE = 3, CTR_QUEUE = 4, CTR_EVENTS = 5,
+  // instrumented hop kernel only: warp residency (ns summed over warps), kernel span as seen from the device
+  // (~first start and last exit, stored for atomicMax), number of warps, lane-iterations with / without an exciton
+  CTR_WARP_NS = 8, CTR_T_FIRST_INV = 9, CTR_T_LAST = 10, CTR_WARPS = 11, CTR_LANE_BUSY = 12, CTR_LANE_IDLE = 13,
+  CTR_COUNT = 16
+};
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -184,6 +195,7 @@ struct KuboArgs {
   int32_t             trace_cap;
   int32_t*            flags;
   unsigned long long* counters;
+  unsigned long long* warp_times;  // diagnostics (instrumented kernel): [warps][4] = enter, first failed take, exit, role
 };
 
 // Persistent warps; every lane owns one exciton at a time, carries it through all nsteps time steps of the launch, files
@@ -212,6 +224,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
   uint32_t       ev0 = 0;
   int32_t*       trace = nullptr;
   int32_t        trace_base = 0;
+  unsigned long long t_enter = 0, it_busy = 0, it_idle = 0, t_dry = 0;
+  if (kInstr) t_enter = global_ns();
 
   auto start = [&]() {
     const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject;
@@ -242,6 +256,9 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
     }
     while (__any_sync(kFullMask, have)) {
       bool finished = false;
+      if (kInstr) {
+        if (have) ++it_busy; else ++it_idle;
+      }
       // One iteration = up to two operations per lane: first the end of a time step for the lanes whose free flight
       // outlasts the step, then a scattering event for the lanes whose flight ends inside the (possibly new) step.
       // The warp pays the latency of both code paths anyway whenever both kinds are present, so a lane that ends a
@@ -289,6 +306,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
             start();
           }
         }
+        if (kInstr && t_dry == 0 && __any_sync(kFullMask, finished && !got)) t_dry = global_ns();
       }
     }
   }
@@ -298,9 +316,23 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
   if (kInstr) {
     const unsigned nc = __reduce_add_sync(kFullMask, L.ncross);
     const unsigned np = __reduce_add_sync(kFullMask, L.nprobe);
+    const unsigned long long t_exit = global_ns();
+    atomicAdd(a.counters + CTR_LANE_BUSY, it_busy);
+    atomicAdd(a.counters + CTR_LANE_IDLE, it_idle);
     if (lane == 0) {
       if (nc) atomicAdd(a.counters + CTR_CROSS, (unsigned long long)nc);
       if (np) atomicAdd(a.counters + CTR_PROBE, (unsigned long long)np);
+      atomicAdd(a.counters + CTR_WARP_NS, t_exit - t_enter);
+      atomicMax(a.counters + CTR_T_FIRST_INV, ~t_enter);
+      atomicMax(a.counters + CTR_T_LAST, t_exit);
+      atomicAdd(a.counters + CTR_WARPS, 1ULL);
+      if (a.warp_times) {
+        unsigned long long* w = a.warp_times + 4 * ((size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5));
+        w[0] = t_enter;
+        w[1] = t_dry ? t_dry : t_exit;
+        w[2] = t_exit;
+        w[3] = hot_role ? 1 : 0;
+      }
     }
   }
 }
