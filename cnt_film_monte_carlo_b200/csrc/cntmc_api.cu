@@ -1281,6 +1281,7 @@ int cntmc_sync(cntmc_t* h) {
     unsigned long long ctrs[CTR_COUNT];
     h->d_counters.download(ctrs, CTR_COUNT, h->stream);
     check_flags(h);  // synchronises the stream, raises what the asynchronous calls could not report
+    if (h->contact_mode) h->hops = (int64_t)ctrs[CTR_EVENTS];
     h->reinjections = (int64_t)ctrs[CTR_REINJECT];
     h->crossings = (int64_t)ctrs[CTR_CROSS];
     h->probes = (int64_t)ctrs[CTR_PROBE];

@@ -48,3 +48,27 @@ class ShardedKubo:
     def msd(self, local_sums: np.ndarray) -> np.ndarray:
         """Ensemble average over the WHOLE population from this rank's local sums (monte_carlo.cpp:402-404)."""
         return allreduce_sums(np.asarray(local_sums, np.float64), self.group) / float(self.total)
+
+
+class ShardedContacts:
+    """One rank's part of a contact-mode run (monte_carlo::init / step / save_metrics / repopulate_contacts).
+
+    The contact rules are per exciton, so the populations the contacts are held at are split statically over the ranks
+    (`c1_pop`, `c2_pop` = this rank's share, the first ranks hold the remainders) and every rank runs its own excitons
+    on a full copy of the film.  Streams must differ between ranks: `seed` mixes the rank into the run's seed.  Unlike
+    the Green-Kubo flavour the trajectories depend on the number of ranks (birth order defines the exciton ids); the
+    ensemble is the same.  The one exchange per engine call is the sum of the integer bins
+    [nsteps][n_seg populations + (n_seg - 1) net crossings] (monte_carlo.h:566-573, 626-636)."""
+
+    def __init__(self, c1_pop: int, c2_pop: int, seed: int, rank: int, world: int, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.c1_pop = shard_range(c1_pop, rank, world)[1]
+        self.c2_pop = shard_range(c2_pop, rank, world)[1]
+        self.seed = (int(seed) + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
+
+    def bins(self, local_bins):
+        """Whole-ensemble bins from this rank's (numpy [nsteps][2*n_seg-1] int64, or a CUDA tensor filled by
+        cntmc_step_dev, reduced in place over NCCL)."""
+        if isinstance(local_bins, np.ndarray):
+            return allreduce_sums(np.asarray(local_bins, np.int64), self.group)
+        return allreduce_sums(local_bins, self.group)

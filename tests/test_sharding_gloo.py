@@ -66,3 +66,48 @@ def test_two_ranks_equal_one(tmp_path):
     for p in parts:
         assert np.allclose(p["msd"], msd, rtol=1e-12, atol=0)                                # only the summation order moves
     assert np.array_equal(parts[0]["msd"], parts[1]["msd"])
+
+
+def contact_worker(rank, world, port, c1, c2, seed, nsteps, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from cnt_film_monte_carlo_b200.parallel import ShardedContacts
+    from oracle import t1 as T1m
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = Golden("small_forster")
+    sc = ShardedContacts(c1, c2, seed, rank, world)
+    t = T1m.T1()
+    t.draws_philox(sc.seed)
+    t.set_memo(True)
+    t.contacts_init(g.mc, g.pos_nm, g.orient, c1_pop=sc.c1_pop, c2_pop=sc.c2_pop)
+    alive = [t.L.t1_num_particles(t.h)]
+    local = []
+    for _ in range(nsteps):
+        pop, cur = t.contact_iteration(1e-14)
+        local.append(np.concatenate([pop, cur]))
+        alive.append(t.L.t1_num_particles(t.h))
+    local = np.array(local, np.int64)
+    total = sc.bins(local.copy())
+    np.savez(os.path.join(out_dir, f"contact_rank{rank}.npz"), local=local, total=total, alive=np.array(alive), c1=sc.c1_pop, c2=sc.c2_pop,
+             seed=np.uint64(sc.seed))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_contact_mode_two_ranks(tmp_path):
+    """Contact populations are split over the ranks, the integer bins are all-reduced: every exciton alive on any rank is
+    counted exactly once per step, both ranks see the same totals, and the shares add up to the requested populations."""
+    c1, c2, nsteps = 301, 40, 30
+    mp.spawn(contact_worker, args=(2, free_port(), c1, c2, 5, nsteps, str(tmp_path)), nprocs=2, join=True)
+    parts = [np.load(tmp_path / f"contact_rank{r}.npz") for r in range(2)]
+    g = Golden("small_forster")
+    n_seg = int(g.mc["number of segments"])
+    assert int(parts[0]["c1"]) + int(parts[1]["c1"]) == c1 and int(parts[0]["c2"]) + int(parts[1]["c2"]) == c2
+    assert int(parts[0]["seed"]) != int(parts[1]["seed"])
+    assert np.array_equal(parts[0]["total"], parts[1]["total"])
+    assert np.array_equal(parts[0]["total"], parts[0]["local"] + parts[1]["local"])
+    alive = parts[0]["alive"] + parts[1]["alive"]
+    assert np.array_equal(parts[0]["total"][:, :n_seg].sum(axis=1), alive[:-1])      # counted before the contacts are refilled
+    assert not np.array_equal(parts[0]["local"], parts[1]["local"])                   # different streams
