@@ -1,6 +1,7 @@
 """Build the engine in-tree: libcntmc.so (nvcc, sm_100a) and the C++ driver cntmc_main (g++, links the library).
 
     python -m cnt_film_monte_carlo_b200.build [--force] [--verbose]
+    python -m cnt_film_monte_carlo_b200.build --segments      # diagnostics twin libcntmc_seg.so (tools/segments.py)
 
 -fmad=false and -ffp-contract=off are part of the arithmetic contract (bit parity with the reference needs unfused
 multiply-adds; the path is not FLOP-bound, so this costs nothing measurable).
@@ -47,6 +48,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_segments() -> str:
+    """Diagnostics build with per-segment cycle counters in the hop loop (tools/segments.py): libcntmc_seg.so."""
+    out = os.path.join(HERE, "libcntmc_seg.so")
+    subprocess.check_call([NVCC, *FLAGS, "-DCNTMC_PROFILE_SEGMENTS", "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]])
+    return out
+
+
 def build_driver(force: bool = False) -> str:
     """cpp/main.cpp + cpp/monte_carlo.hpp: the reference-shaped C++ host side over the C ABI."""
     deps = [os.path.join(CPP, "main.cpp"), os.path.join(CPP, "monte_carlo.hpp"), os.path.join(CSRC, "json_min.h"),
@@ -58,6 +66,9 @@ def build_driver(force: bool = False) -> str:
 
 
 if __name__ == "__main__":
+    if "--segments" in sys.argv:
+        print(build_segments())
+        sys.exit(0)
     build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(LIB)
     print(DRIVER)

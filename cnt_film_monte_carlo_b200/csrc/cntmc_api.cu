@@ -451,7 +451,7 @@ void launch_kubo(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) 
     if (dump && *dump) {
       KuboArgs                   b = a;
       DevBuf<unsigned long long> d_times;
-      const size_t               n = (size_t)grid * 4 * 4;
+      const size_t               n = (size_t)grid * 4 * kWarpTimeCols;
       d_times.alloc(n);
       CUDA_CHECK(cudaMemsetAsync(d_times.p, 0, n * sizeof(unsigned long long), st));
       b.warp_times = d_times.p;

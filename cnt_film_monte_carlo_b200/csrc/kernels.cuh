@@ -176,6 +176,11 @@ __device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, boo
   return got;
 }
 
+#if defined(CNTMC_PROFILE_SEGMENTS)
+constexpr int kWarpTimeCols = 12;  // + cycles per loop segment of lane 0
+#else
+constexpr int kWarpTimeCols = 4;
+#endif
 struct alignas(32) StageRec {  // one full 32-byte sector per (step, exciton)
   double dx2, dy2, dz2, events;
 };
@@ -225,7 +230,11 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
   int32_t*       trace = nullptr;
   int32_t        trace_base = 0;
   unsigned long long t_enter = 0, it_busy = 0, it_idle = 0, t_dry = 0;
+  int                iter = 0;
   if (kInstr) t_enter = global_ns();
+#if defined(CNTMC_PROFILE_SEGMENTS)
+  L.seg_t = clock64();
+#endif
 
   auto start = [&]() {
     const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject;
@@ -258,11 +267,13 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
       bool finished = false;
       if (kInstr) {
         if (have) ++it_busy; else ++it_idle;
+        ++iter;
       }
       // One iteration = up to two operations per lane: first the end of a time step for the lanes whose free flight
       // outlasts the step, then a scattering event for the lanes whose flight ends inside the (possibly new) step.
       // The warp pays the latency of both code paths anyway whenever both kinds are present, so a lane that ends a
       // step and scatters right away gets both done in the same pass.
+      CNTMC_SEG(L, 6);  // loop head, refill
       if (have && !(L.ff <= dt_rem)) {  // particle.cpp:62 false: the flight outlasts the step
         const double t = dt_rem;
         const Leg    leg = fly(L, a.T, t, true);
@@ -279,12 +290,14 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
         ev0 = L.nevent;
         finished = (step >= a.nsteps);
       }
+      CNTMC_SEG(L, 5);  // step-end path (own, or waiting for the lanes that run it)
       if (have && !finished && (L.ff <= dt_rem)) {
         const double t = L.ff;
         const Leg    leg = fly(L, a.T, t, false);
         dt_rem -= t;  // particle.cpp:63
         after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u);
       }
+      CNTMC_SEG(L, 7);  // waiting for the other lanes of the warp to finish their events
       finished = have && (finished || L.stuck);
       if (__any_sync(kFullMask, finished)) {
         int cls = 0;
@@ -327,11 +340,14 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
       atomicMax(a.counters + CTR_T_LAST, t_exit);
       atomicAdd(a.counters + CTR_WARPS, 1ULL);
       if (a.warp_times) {
-        unsigned long long* w = a.warp_times + 4 * ((size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5));
+        unsigned long long* w = a.warp_times + kWarpTimeCols * ((size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5));
         w[0] = t_enter;
         w[1] = t_dry ? t_dry : t_exit;
         w[2] = t_exit;
-        w[3] = hot_role ? 1 : 0;
+        w[3] = (hot_role ? 1ull : 0ull) | ((unsigned long long)iter << 8);
+#if defined(CNTMC_PROFILE_SEGMENTS)
+        for (int k = 0; k < 8; ++k) w[4 + k] = (unsigned long long)L.seg[k];  // lane 0 of the warp
+#endif
       }
     }
   }

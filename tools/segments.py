@@ -1,5 +1,5 @@
 """Cycles per segment of the hop loop, lane 0 of every warp, one instrumented 64-step launch of a diagnostics build
-(-DCNTMC_PROFILE_SEGMENTS; run with CNTMC_LIB=<that build>)."""
+(python -m cnt_film_monte_carlo_b200.build --segments; run with CNTMC_LIB=cnt_film_monte_carlo_b200/libcntmc_seg.so)."""
 import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,7 @@ from bench import mc_block, DT
 P = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
 pos, ori = film.film(**film.CONFIG_FILMS["C2"])
 e = Engine(mc_block(P)); e.set_mesh(pos, ori)
-for k in ("park_s", "park_s_lanes", "park_e", "park_e_lanes", "hot_pct", "chunk_steps"):
+for k in ("hot_pct", "chunk_steps", "occupancy"):
     if os.environ.get(k.upper()):
         e.set_option(k, int(os.environ[k.upper()]))
 e.kubo_init(); e.kubo_create_particles(P, seed=1)
@@ -20,7 +20,7 @@ e.set_option("stats", 1)
 e.kubo_step(DT, 64, want_msd=False)
 raw = np.fromfile(path, dtype=np.uint64).reshape(-1, 12)
 role = (raw[:, 3] & np.uint64(1)).astype(int)
-iters = ((raw[:, 3] >> np.uint64(8)) & np.uint64(0xffffff)).astype(np.float64)
+iters = (raw[:, 3] >> np.uint64(8)).astype(np.float64)
 seg = raw[:, 4:].astype(np.float64)
 names = ["E: fly", "E: hop info + draw + dice", "E: select (row probes)", "E: set_site / move", "E: ff (draw, log, 1/Gamma of dest)",
          "S: step-end path", "loop head / refill", "wait for the warp after own event"]

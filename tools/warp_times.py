@@ -16,11 +16,15 @@ path = "/tmp/warp_times.bin"
 os.environ["CNTMC_DEBUG_WARP_TIMES"] = path
 e.set_option("stats", 1)
 e.kubo_step(DT, 64, want_msd=False)
-w = np.fromfile(path, dtype=np.uint64).reshape(-1, 4).astype(np.float64)
+raw = np.fromfile(path, dtype=np.uint64).reshape(-1, 4)
+w = raw.astype(np.float64)
 t0 = w[:, 0].min()
-dry, ex, role = (w[:, 1] - t0) / 1e6, (w[:, 2] - t0) / 1e6, w[:, 3]
+dry, ex, role = (w[:, 1] - t0) / 1e6, (w[:, 2] - t0) / 1e6, (raw[:, 3] & np.uint64(1)).astype(np.float64)
+iters = (raw[:, 3] >> np.uint64(8)).astype(np.float64)
 out = {"P": P, "hot_pct": hot, "span_ms": float(ex.max())}
 for name, m in (("hot", role == 1), ("cold", role == 0)):
     out[name] = {"warps": int(m.sum()), "first_dry_ms_pct": [float(np.percentile(dry[m], q)) for q in (0, 10, 50, 90, 100)],
-                 "exit_ms_pct": [float(np.percentile(ex[m], q)) for q in (0, 10, 50, 90, 99, 100)]}
+                 "exit_ms_pct": [float(np.percentile(ex[m], q)) for q in (0, 10, 50, 90, 99, 100)],
+                 "iterations_pct": [float(np.percentile(iters[m], q)) for q in (10, 50, 90, 100)],
+                 "us_per_iteration_pct": [float(np.percentile(1e3 * ex[m] / np.maximum(iters[m], 1), q)) for q in (10, 50, 90)]}
 print(json.dumps(out))
