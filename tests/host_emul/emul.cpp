@@ -278,12 +278,8 @@ int64_t emul_select_guided(const double* cum, int64_t d, int32_t r) {
   uint32_t g[2];
   memcpy(g, g8, sizeof(g));
   const double dice = total * (double)r / kRandMax;
-  uint32_t     lo = 0, hi = (uint32_t)d - 1;
-  if ((uint32_t)d <= kGuideMaxRow) {
-    const uint32_t j = (uint32_t)r >> kGuideShift;
-    lo = guide_byte(g[0], g[1], j);
-    if (j + 1 < (uint32_t)kGuideBuckets) hi = guide_byte(g[0], g[1], j + 1);
-  }
+  uint32_t     lo, hi;
+  guide_bracket(g[0], g[1], (uint32_t)d, r, lo, hi);
   return select_via_entries(cum, d, lo, hi, dice);
 }
 int64_t emul_select_full(const double* cum, int64_t d, double dice) { return select_via_entries(cum, d, 0u, (uint32_t)d - 1u, dice); }

@@ -98,7 +98,7 @@ def test_guided_search_equals_reference_loop_for_every_bucket():
     e.L.emul_select_guided.restype = __import__("ctypes").c_int64
     e.L.emul_select_guided.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int64, __import__("ctypes").c_int32]
     for _ in range(1500):
-        d = int(rng.integers(1, 300))  # rows above 255 entries bypass the guide
+        d = int(rng.integers(1, 300)) if _ % 3 else int(rng.integers(250, 3000))  # long rows store scaled guide entries
         c = np.ascontiguousarray(np.cumsum(rng.random(d) ** 8 * (rng.random(d) > 0.2) * 10.0 ** rng.integers(8, 15)))
         if c[-1] == 0:
             continue
