@@ -22,6 +22,7 @@ struct Emul {
   Buckets              buckets;
   Injection            inj;
   std::vector<SiteRec> site;
+  std::vector<TopRec>  top;
   std::vector<PosRec>  pos;
   std::vector<double>  cum;
   std::vector<int32_t> nbr;
@@ -34,7 +35,8 @@ struct Emul {
   std::vector<int32_t> r_draws;
   std::vector<double>  r_logs;
   bool                 replay = false;
-  int64_t              guards = 0, hops = 0;
+  int64_t              guards = 0, hops = 0, fast = 0;
+  bool                 fast_path = false;  // decide events by the top entries of the site record where possible
   std::string          err;
   std::vector<std::vector<int32_t>> trace;
 };
@@ -73,6 +75,7 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
     const int64_t n = e->sites.N;
     std::vector<SiteGeom> geom((size_t)n);
     e->site = make_site_records(e->sites, e->prm.velocity, e->pos);
+    e->top.assign(e->site.size(), TopRec{});
     for (int64_t i = 0; i < n; ++i) {
       geom[i] = SiteGeom{e->sites.pos[0][i], e->sites.pos[1][i], e->sites.pos[2][i],
                          e->sites.orient[0][i], e->sites.orient[1][i], e->sites.orient[2][i]};
@@ -91,6 +94,8 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
       uint32_t d = 0;
       double   acc = 0;
       bool     guard = false;
+      TopEntries top;
+      top.clear();
       for (int ix = cx - 1; ix <= cx + 1; ++ix)
         for (int iy = cy - 1; iy <= cy + 1; ++iy)
           for (int iz = cz - 1; iz <= cz + 1; ++iz) {
@@ -100,7 +105,9 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
               const SiteGeom& s2 = geom[e->buckets.sites[q]];
               if (!within_cutoff(s1, s2, radius)) continue;
               const double rate = pair_rate(s1, s2, R, &guard);
+              const double below = (d == 0) ? -1.0 : acc;
               acc = (d == 0) ? rate : acc + rate;
+              top.add(rate, below, acc, e->buckets.sites[q]);
               e->nbr.push_back(e->buckets.sites[q]);
               e->cum.push_back(acc);
               ++d;
@@ -116,8 +123,10 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
       }
       e->site[i].row_begin = (uint32_t)e->row_ptr[i];
       e->site[i].row_len = d;
+      top.store(e->top[i]);
       e->guards += guard;
     }
+    e->T.top = e->top.data();
     e->T.site = e->site.data();
     e->T.pos = e->pos.data();
     e->row.resize(e->cum.size());
@@ -219,10 +228,11 @@ static int step(Emul* e, double dt, int64_t nsteps, double* msd, int trace_cap) 
     Cursor c;
     init_draws(e, D, i);
     L.nevent = 0;
+    L.nfast = 0;
     c.step = 0;
     begin_step(c, L, dt);
     while (c.step < nsteps && !L.stuck) {
-      if (advance(L, e->T, D, c, trace_cap > 0 ? tr.data() : nullptr, (uint32_t)trace_cap)) {
+      if (advance(L, e->T, D, c, trace_cap > 0 ? tr.data() : nullptr, (uint32_t)trace_cap, e->fast_path)) {
         sums[c.step * 3 + 0] += L.dx * L.dx;
         sums[c.step * 3 + 1] += L.dy * L.dy;
         sums[c.step * 3 + 2] += L.dz * L.dz;
@@ -231,6 +241,7 @@ static int step(Emul* e, double dt, int64_t nsteps, double* msd, int trace_cap) 
       }
     }
     e->hops += L.nevent;
+    e->fast += L.nfast;
     if (trace_cap > 0) e->trace[i].insert(e->trace[i].end(), tr.begin(), tr.begin() + std::min<uint32_t>(L.nevent, trace_cap));
     bad |= L.stuck || D.exhausted();
   }
@@ -243,6 +254,8 @@ int emul_kubo_step(Emul* e, double dt, int64_t nsteps, double* msd, int trace_ca
   return e->replay ? step<ReplayDraws>(e, dt, nsteps, msd, trace_cap) : step<PhiloxDraws>(e, dt, nsteps, msd, trace_cap);
 }
 int64_t emul_hops(Emul* e) { return e->hops; }
+int64_t emul_fast_events(Emul* e) { return e->fast; }
+void emul_set_fast_path(Emul* e, int on) { e->fast_path = on != 0; }
 void emul_particles(Emul* e, int32_t* site, double* pos, double* delta, double* ff, int32_t* heading, uint32_t* ndraw) {
   const size_t P = e->lanes.size();
   for (size_t i = 0; i < P; ++i) {
@@ -281,6 +294,18 @@ int64_t emul_select_guided(const double* cum, int64_t d, int32_t r) {
   uint32_t     lo, hi;
   guide_bracket(g[0], g[1], (uint32_t)d, r, lo, hi);
   return select_via_entries(cum, d, lo, hi, dice);
+}
+// the decision of fast_event: index of the top entry whose interval holds dice, or -1 (ordinary search needed)
+int64_t emul_select_top(const double* cum, int64_t d, double dice) {
+  TopEntries top;
+  top.clear();
+  for (int64_t k = 0; k < d; ++k) top.add(k ? cum[k] - cum[k - 1] : cum[0], k ? cum[k - 1] : -1.0, cum[k], (int32_t)k);
+  TopRec r{};
+  top.store(r);
+  if (r.lo0 <= dice && dice < r.hi0) return r.nbr[0];
+  if (r.lo1 <= dice && dice < r.hi1) return r.nbr[1];
+  if (r.lo2 <= dice && dice < r.hi2) return r.nbr[2];
+  return -1;
 }
 int64_t emul_select_full(const double* cum, int64_t d, double dice) { return select_via_entries(cum, d, 0u, (uint32_t)d - 1u, dice); }
 void emul_philox2x32(uint32_t c0, uint32_t c1, uint32_t k, uint32_t* out) { philox2x32_10(c0, c1, k, out); }

@@ -92,6 +92,54 @@ def test_select_entry_equals_reference_loop():
             assert e.L.emul_select_full(c.ctypes.data, d, ctypes.c_double(dice)) == T1m.select(c, dice)  # the engine's entry search
 
 
+def test_top_entries_decide_exactly_what_the_reference_loop_decides():
+    """fast_event's shortcut: a dice inside the interval of one of the three widest entries selects that entry."""
+    import ctypes
+    e = Emul(base_mc())
+    e.L.emul_select_top.restype = ctypes.c_int64
+    e.L.emul_select_top.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double]
+    rng = np.random.default_rng(23)
+    decided = 0
+    for _ in range(3000):
+        d = int(rng.integers(1, 60))
+        rates = rng.random(d) * (rng.random(d) > 0.25)
+        rates[rng.integers(0, d, size=int(rng.integers(0, 4)))] *= 1e3   # a few dominant entries, as on hot sites
+        c = np.cumsum(rates)
+        for dice in (0.0, c[-1], c[-1] * rng.random(), float(rng.choice(c)), np.nextafter(float(rng.choice(c)), 0), np.nextafter(float(rng.choice(c)), np.inf)):
+            k = e.L.emul_select_top(c.ctypes.data, d, ctypes.c_double(dice))
+            if k >= 0:
+                assert k == T1m.select(c, dice)
+                decided += 1
+    assert decided > 4000
+
+
+def test_fast_event_path_is_bit_identical_and_matches_oracle(golden):
+    """Events decided by the top entries of the site record (the kernel's fast loop) change nothing."""
+    res = []
+    for on in (False, True):
+        e = Emul(golden.mc)
+        e.kubo_init(golden.pos_nm, golden.orient)
+        e.set_fast_path(on)
+        e.create_philox(96, seed=77, first_gid=500)
+        msd = e.kubo_step(golden.dt, 150, trace_cap=1 << 14)
+        res.append((e.particles(), msd, e.trace(), e.hops(), e.fast_events()))
+    (pa, ma, (oa, fa), ha, _), (pb, mb, (ob, fb), hb, nfast) = res
+    assert all(np.array_equal(pa[k], pb[k]) for k in pa) and np.array_equal(ma, mb)
+    assert np.array_equal(oa, ob) and np.array_equal(fa, fb) and ha == hb
+    assert nfast > 0.3 * hb, (nfast, hb)   # the shortcut is actually taken
+    t = T1m.T1()
+    t.kubo_init(golden.mc, golden.pos_nm, golden.orient)
+    t.draws_philox(77)
+    t.trace_sites(True)
+    t.create_particles(96, first_global_id=500)
+    t.kubo_step(golden.dt, 150)
+    pt = t.particles()
+    for k in STATE_KEYS:
+        assert np.array_equal(pb[k], pt[k]), k
+    off_t, flat_t = t.traced_sites(596)
+    assert np.array_equal(np.diff(off_t)[500:], np.diff(ob)) and np.array_equal(flat_t, fb)
+
+
 def test_guided_search_equals_reference_loop_for_every_bucket():
     e = Emul(base_mc())
     rng = np.random.default_rng(5)
