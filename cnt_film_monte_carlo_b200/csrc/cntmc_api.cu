@@ -988,6 +988,7 @@ static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned 
     a.dt = dt;
     a.nsteps = n;
     a.n_seg = h->n_seg;
+    a.use_top = h->opt_fast_rounds > 0 ? 1 : 0;
     a.ymin = h->dom.lo[1];
     a.ymax = h->dom.hi[1];
     a.dy = (h->dom.hi[1] - h->dom.lo[1]) / double(h->n_seg);  // monte_carlo.h:446

@@ -38,19 +38,21 @@ struct DrawConfig {
   const double*  replay_logs;
 };
 
+// Exciton state streams through once per launch (ld.cs).  kCoherent: read through L2 only (ld.cg) -- in the two-engine
+// kernel an exciton may come back to an SM that has seen an older version of it, and L1 is not coherent.
+template <bool kCoherent = false>
 __device__ __forceinline__ void load_lane(Lane& L, const ExcitonArrays& S, const Tables& T, int64_t e) {
-  // exciton state is read through L2 only (ld.cg): it streams through once per launch, and in the two-engine kernel an
-  // exciton may come back to an SM that has seen an older version of it (L1 is not coherent)
-  L.px = __ldcg(S.px + e);
-  L.py = __ldcg(S.py + e);
-  L.pz = __ldcg(S.pz + e);
-  L.dx = __ldcg(S.dx + e);
-  L.dy = __ldcg(S.dy + e);
-  L.dz = __ldcg(S.dz + e);
-  L.ff = __ldcg(S.ff + e);
-  L.site = __ldcg(S.site + e);
-  L.heading_right = __ldcg(S.heading + e) != 0;
-  L.ndraw = __ldcg(S.ndraw + e);
+  auto ld = [](auto* p) { return kCoherent ? __ldcg(p) : __ldcs(p); };
+  L.px = ld(S.px + e);
+  L.py = ld(S.py + e);
+  L.pz = ld(S.pz + e);
+  L.dx = ld(S.dx + e);
+  L.dy = ld(S.dy + e);
+  L.dz = ld(S.dz + e);
+  L.ff = ld(S.ff + e);
+  L.site = ld(S.site + e);
+  L.heading_right = ld(S.heading + e) != 0;
+  L.ndraw = ld(S.ndraw + e);
   L.nevent = 0;
   L.stuck = false;
   attach_site(L, T);
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_engines_kernel(const Kub
 
   auto start = [&](bool resumed, bool event_engine) {
     const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject, nf = L.nfast;
-    load_lane(L, a.S, a.T, (int64_t)e);
+    load_lane<true>(L, a.S, a.T, (int64_t)e);
     L.ncross = nc;
     L.nprobe = np;
     L.nreinject = nr;
@@ -822,6 +824,7 @@ struct ContactArgs {
   double              dt;
   int32_t             nsteps;
   int32_t             n_seg;
+  int32_t             use_top;  // try the three widest entries of a row before searching it
   double              ymin, ymax, dy;
   unsigned long long* bins;  // [nsteps][2*n_seg-1]: population per slab, then net crossings per interface
   int32_t*            flags;
@@ -873,7 +876,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) contact_kernel(const ContactA
   while (__any_sync(kFullMask, have)) {
     bool finished = false;
     if (have) {
-      if (c.step < a.nsteps && advance_contact(L, a.T, D, c)) {
+      if (c.step < a.nsteps && advance_contact(L, a.T, D, c, a.use_top != 0)) {
         int* h = hist + c.step * nb;
         atomicAdd(h + y_slab(L.py, a.ymin, a.dy, a.n_seg), 1);  // monte_carlo.h:566-573
         for (int k = 1; k < a.n_seg; ++k) {                      // monte_carlo.h:626-636
