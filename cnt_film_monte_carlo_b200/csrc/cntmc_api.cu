@@ -143,12 +143,6 @@ struct cntmc_handle {
   // device tables
   DevBuf<SiteRec> d_site;
   DevBuf<TopRec> d_top;
-  // two-engine hop kernel: hand-over queues, their counters {head0, tail0, head1, tail1, remaining}, cursors
-  DevBuf<unsigned long long> d_ring_cell[2], d_ring_ctr;
-  uint32_t                   ring_cap = 0;
-  DevBuf<int32_t>            d_cur_step;
-  DevBuf<double>             d_cur_dt, d_cur_ox, d_cur_oy, d_cur_oz;
-  DevBuf<uint32_t>           d_cur_ev;
   DevBuf<PosRec>  d_pos;
   DevBuf<RowEntry> d_row;
   DevBuf<int32_t>  d_inject, d_c1, d_c2;
@@ -188,9 +182,6 @@ struct cntmc_handle {
   // tuning
   int64_t opt_chunk = 64;     // time steps per launch
   int64_t opt_sort = 1;       // (kept for compatibility; activity classes replaced the sort)
-  int64_t opt_engines = 0;      // 1: hop kernel with specialised flight / event warps and in-launch hand-over (measured slower: off)
-  int64_t opt_refill_min = 4;  // idle lanes that make a warp of the two-engine kernel fetch new excitons
-  int64_t opt_park_min = 4, opt_park_max = 8;  // flight warps gather this many due events, or wait this many iterations
   int64_t opt_fast_rounds = 1;  // 0: row search only; 1: the row's three widest entries are tried first; n > 1: plus n-1 rounds of fast_event per iteration
   int64_t opt_hot_pct = 30;   // share of the blocks that serve the most active classes first
   int64_t opt_block = 128;  // threads per block of the hop kernel
@@ -447,14 +438,6 @@ __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p
 
 template <typename Draws, bool kInstr>
 void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) {
-  if (h->opt_engines) {
-    switch (h->opt_occupancy) {
-      case 4: kubo_engines_kernel<Draws, 4, kInstr><<<grid, 128, 0, st>>>(a); break;
-      case 6: kubo_engines_kernel<Draws, 6, kInstr><<<grid, 128, 0, st>>>(a); break;
-      default: kubo_engines_kernel<Draws, 5, kInstr><<<grid, 128, 0, st>>>(a); break;
-    }
-    return;
-  }
   switch (h->opt_occupancy) {
     case 4: kubo_kernel<Draws, 4, kInstr><<<grid, 128, 0, st>>>(a); break;
     case 6: kubo_kernel<Draws, 6, kInstr><<<grid, 128, 0, st>>>(a); break;
@@ -523,22 +506,6 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     h->d_list_count[b].alloc(kClasses);
   }
   h->d_list_head.alloc(kClasses);
-  if (h->opt_engines) {  // hand-over queues: capacity >= P (an exciton waits in at most one), counters keep counting
-    uint32_t cap = 1024;
-    while ((int64_t)cap < h->P) cap <<= 1;
-    if (cap != h->ring_cap) {
-      h->d_ring_ctr.alloc(16 * 8);  // head0, tail0, head1, tail1, remaining, avail0, avail1: one 128-byte line each
-      CUDA_CHECK(cudaMemsetAsync(h->d_ring_ctr.p, 0, 16 * 8 * sizeof(unsigned long long), st));
-      for (int r = 0; r < 2; ++r) {
-        h->d_ring_cell[r].alloc(cap);
-        ring_init_kernel<<<(cap + 255) / 256, 256, 0, st>>>(h->d_ring_cell[r].p, cap, 0ULL);
-      }
-      CUDA_CHECK(cudaGetLastError());
-      h->ring_cap = cap;
-    }
-    h->d_cur_step.alloc((size_t)h->P); h->d_cur_dt.alloc((size_t)h->P); h->d_cur_ox.alloc((size_t)h->P);
-    h->d_cur_oy.alloc((size_t)h->P); h->d_cur_oz.alloc((size_t)h->P); h->d_cur_ev.alloc((size_t)h->P);
-  }
   auto lists = [&](int read_buf) {
     ClassLists q{};
     for (int c = 0; c < kClasses; ++c) {
@@ -570,18 +537,6 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     a.q = lists(h->cur_list);
     a.hot_blocks = (int32_t)((int64_t)grid * h->opt_hot_pct / 100);
     a.fast_rounds = (int32_t)h->opt_fast_rounds;
-    a.refill_min = (int32_t)h->opt_refill_min;
-    a.park_min = (int32_t)h->opt_park_min;
-    a.park_max = (int32_t)h->opt_park_max;
-    if (h->opt_engines) {
-      for (int r = 0; r < 2; ++r) a.ring[r] = Ring{h->d_ring_cell[r].p, h->d_ring_ctr.p + 32 * r, h->d_ring_ctr.p + 32 * r + 16,
-                                                   reinterpret_cast<long long*>(h->d_ring_ctr.p + 80 + 16 * r), h->ring_cap - 1};
-      a.remaining = h->d_ring_ctr.p + 64;
-      // the event engine's dedicated blocks never serve flights: leave at least a tenth of the grid free
-      a.hot_blocks = std::min<int32_t>(a.hot_blocks, (int32_t)grid - std::max<int32_t>(1, (int32_t)grid / 10));
-      a.cur = Cursors{h->d_cur_step.p, h->d_cur_dt.p, h->d_cur_ox.p, h->d_cur_oy.p, h->d_cur_oz.p, h->d_cur_ev.p};
-      set_u64_kernel<<<1, 1, 0, st>>>(a.remaining, (unsigned long long)h->P);
-    }
     a.P = h->P;
     a.dt = dt;
     a.nsteps = n;
@@ -1293,17 +1248,6 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "occupancy") {
       require(value >= 4 && value <= 8, "occupancy must be 4 to 8 blocks per SM");
       h->opt_occupancy = value;
-    } else if (k == "refill_min") {
-      require(value >= 1 && value <= 32, "refill_min must be in [1, 32]");
-      h->opt_refill_min = value;
-    } else if (k == "park_min") {
-      require(value >= 1 && value <= 32, "park_min must be in [1, 32]");
-      h->opt_park_min = value;
-    } else if (k == "park_max") {
-      require(value >= 0 && value <= 1024, "park_max must be in [0, 1024]");
-      h->opt_park_max = value;
-    } else if (k == "engines") {
-      h->opt_engines = value ? 1 : 0;
     } else if (k == "fast_rounds") {
       require(value >= 0 && value <= 64, "fast_rounds must be in [0, 64]");
       h->opt_fast_rounds = value;
@@ -1327,10 +1271,6 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "occupancy") return h->opt_occupancy;
   if (k == "hot_pct") return h->opt_hot_pct;
   if (k == "fast_rounds") return h->opt_fast_rounds;
-  if (k == "engines") return h->opt_engines;
-  if (k == "refill_min") return h->opt_refill_min;
-  if (k == "park_min") return h->opt_park_min;
-  if (k == "park_max") return h->opt_park_max;
   if (k == "stage_mb") return h->opt_stage_mb;
   if (k.rfind("dbg_", 0) == 0) {  // raw device counters of the last instrumented hop-kernel launch (option "stats")
     unsigned long long ctrs[CTR_COUNT];
@@ -1341,10 +1281,6 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
     if (k == "dbg_lane_busy") return (int64_t)ctrs[CTR_LANE_BUSY];
     if (k == "dbg_lane_idle") return (int64_t)ctrs[CTR_LANE_IDLE];
     if (k == "dbg_fast_events") return (int64_t)ctrs[CTR_FAST];
-    if (k.rfind("dbg_phase_", 0) == 0) {  // dbg_phase_<engine><phase>, dbg_phase_it<engine>
-      if (k.size() == 13 && k[10] == 'i') return (int64_t)ctrs[CTR_ITER + (k[12] - '0')];
-      if (k.size() == 12) return (int64_t)ctrs[CTR_PHASE + 6 * (k[10] - '0') + (k[11] - '0')];
-    }
   }
   return -1;
 }

@@ -38,21 +38,17 @@ struct DrawConfig {
   const double*  replay_logs;
 };
 
-// Exciton state streams through once per launch (ld.cs).  kCoherent: read through L2 only (ld.cg) -- in the two-engine
-// kernel an exciton may come back to an SM that has seen an older version of it, and L1 is not coherent.
-template <bool kCoherent = false>
 __device__ __forceinline__ void load_lane(Lane& L, const ExcitonArrays& S, const Tables& T, int64_t e) {
-  auto ld = [](auto* p) { return kCoherent ? __ldcg(p) : __ldcs(p); };
-  L.px = ld(S.px + e);
-  L.py = ld(S.py + e);
-  L.pz = ld(S.pz + e);
-  L.dx = ld(S.dx + e);
-  L.dy = ld(S.dy + e);
-  L.dz = ld(S.dz + e);
-  L.ff = ld(S.ff + e);
-  L.site = ld(S.site + e);
-  L.heading_right = ld(S.heading + e) != 0;
-  L.ndraw = ld(S.ndraw + e);
+  L.px = __ldcs(S.px + e);  // exciton state streams through once per launch
+  L.py = __ldcs(S.py + e);
+  L.pz = __ldcs(S.pz + e);
+  L.dx = __ldcs(S.dx + e);
+  L.dy = __ldcs(S.dy + e);
+  L.dz = __ldcs(S.dz + e);
+  L.ff = __ldcs(S.ff + e);
+  L.site = __ldcs(S.site + e);
+  L.heading_right = __ldcs(S.heading + e) != 0;
+  L.ndraw = __ldcs(S.ndraw + e);
   L.nevent = 0;
   L.stuck = false;
   attach_site(L, T);
@@ -89,8 +85,7 @@ enum {
   // instrumented hop kernel only: warp residency (ns summed over warps), kernel span as seen from the device
   // (~first start and last exit, stored for atomicMax), number of warps, lane-iterations with / without an exciton
   CTR_WARP_NS = 8, CTR_T_FIRST_INV = 9, CTR_T_LAST = 10, CTR_WARPS = 11, CTR_LANE_BUSY = 12, CTR_LANE_IDLE = 13,
-  // two-engine kernel, instrumented: ns per loop phase of lane 0, [engine][phase], and iterations per engine
-  CTR_PHASE = 16, CTR_ITER = 28, CTR_COUNT = 32
+  CTR_COUNT = 16
 };
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -166,10 +161,7 @@ __device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, boo
     const int          n = __popc(need), leader = __ffs(need) - 1;
     const long long    cnt = (long long)q.count[c];
     unsigned long long base = 0;
-    // (an exhausted list is not touched again: idle lanes of the two-engine kernel ask repeatedly)
-    if (lane == leader)
-      base = (cnt > 0 && *(volatile unsigned long long*)(q.head + c) < (unsigned long long)cnt) ? atomicAdd(q.head + c, (unsigned long long)n)
-                                                                                               : (unsigned long long)cnt;
+    if (lane == leader) base = (cnt > 0) ? atomicAdd(q.head + c, (unsigned long long)n) : (unsigned long long)cnt;
     base = __shfl_sync(0xffffffffu, base, leader);
     const long long avail = cnt - (long long)base;
     if (want && !got) {
@@ -184,106 +176,6 @@ __device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, boo
   return got;
 }
 
-
-// ---- hand-over queues of the two-engine hop kernel -----------------------------------------------------------------------
-// A bounded multi-producer multi-consumer queue of exciton indices (Vyukov's scheme, one 64-bit word per cell:
-// sequence number in the high half, exciton index in the low half).  Cell i starts as (i, -); the producer of position
-// p waits for (p, -), publishes (p+1, exciton) with release semantics -- the state it stored for the exciton is visible
-// to whoever reads the cell -- and the consumer of position p waits for (p+1, .), then leaves (p + capacity, -).  The
-// capacity is at least the number of excitons and an exciton waits in at most one queue, so producers never wait.
-// head and tail keep counting from launch to launch.  Consumers read exciton state with ld.cg (L2): L1 is not coherent.
-struct Ring {
-  unsigned long long* cell;
-  unsigned long long* head;
-  unsigned long long* tail;
-  long long*          avail;  // positions produced and not yet claimed by a consumer (a semaphore: no compare-and-swap loops)
-  uint32_t            mask;   // capacity - 1
-};
-struct Cursors {  // where in the launch a handed-over exciton is
-  int32_t*  step;
-  double*   dt_rem;
-  double *  ox, *oy, *oz;  // position at the start of its current time step (_old_pos)
-  uint32_t* ev;            // events since the start of its current time step
-};
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-constexpr int kSpinLimit = 1 << 24;  // polls before a wait is declared stuck (reported by the host; never seen)
-// append exciton e of the lanes flagged `mine` (call with the whole warp; the lanes' state stores come first)
-__device__ __forceinline__ bool ring_push(const Ring& r, bool mine, uint32_t e, int lane, unsigned lt_mask) {
-  const unsigned m = __ballot_sync(0xffffffffu, mine);
-  if (!m) return true;
-  unsigned long long base = 0;
-  const int          leader = __ffs(m) - 1;
-  if (lane == leader) {
-    base = atomicAdd(r.tail, (unsigned long long)__popc(m));
-    atomicAdd((unsigned long long*)r.avail, (unsigned long long)__popc(m));  // consumers wait on the cell for the index itself
-  }
-  base = __shfl_sync(0xffffffffu, base, leader);
-  bool ok = true;
-  if (mine) {
-    const unsigned long long pos = base + (unsigned long long)__popc(m & lt_mask);
-    unsigned long long*      c = r.cell + (pos & r.mask);
-    int                      spin = 0;
-    while ((uint32_t)(ld_relaxed_u64(c) >> 32) != (uint32_t)pos && ++spin < kSpinLimit) {
-    }
-    ok = spin < kSpinLimit;
-    st_release_u64(c, ((unsigned long long)(uint32_t)(pos + 1) << 32) | e);
-  }
-  return ok;
-}
-// hand an exciton to every lane that `want`s one, as far as the queue holds any (call with the whole warp)
-__device__ __forceinline__ bool ring_pop(const Ring& r, bool want, int lane, unsigned lt_mask, uint32_t& e, bool& ok) {
-  const unsigned need = __ballot_sync(0xffffffffu, want);
-  if (!need) return false;
-  const int          leader = __ffs(need) - 1;
-  unsigned long long base = 0;
-  unsigned           take = 0;
-  if (lane == leader && (long long)ld_relaxed_u64((const unsigned long long*)r.avail) > 0) {
-    // claim up to n of the available positions: fetch-and-add, hand back what was not there (thousands of warps use
-    // this word; a compare-and-swap loop would convoy)
-    const long long n = (long long)__popc(need);
-    const long long old = (long long)atomicAdd((unsigned long long*)r.avail, (unsigned long long)(-n));
-    const long long got = old <= 0 ? 0 : (old < n ? old : n);
-    if (got < n) atomicAdd((unsigned long long*)r.avail, (unsigned long long)(n - got));
-    if (got > 0) {
-      base = atomicAdd(r.head, (unsigned long long)got);
-      take = (unsigned)got;
-    }
-  }
-  base = __shfl_sync(0xffffffffu, base, leader);
-  take = __shfl_sync(0xffffffffu, take, leader);
-  bool got = false;
-  if (want && (unsigned)__popc(need & lt_mask) < take) {
-    const unsigned long long pos = base + (unsigned long long)__popc(need & lt_mask);
-    unsigned long long*      c = r.cell + (pos & r.mask);
-    unsigned long long       v;
-    int                      spin = 0;
-    while ((uint32_t)((v = ld_relaxed_u64(c)) >> 32) != (uint32_t)(pos + 1) && ++spin < kSpinLimit) {
-    }
-    if (spin >= kSpinLimit) ok = false;
-    e = (uint32_t)(v & 0xffffffffULL);
-    st_relaxed_u64(c, (unsigned long long)(uint32_t)(pos + (unsigned long long)r.mask + 1ULL) << 32);
-    got = true;
-  }
-  return got;
-}
-__device__ __forceinline__ bool ring_has_work(const Ring& r) { return (long long)ld_relaxed_u64((const unsigned long long*)r.avail) > 0; }
-__global__ void ring_init_kernel(unsigned long long* cell, uint32_t capacity, unsigned long long first) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= capacity) return;
-  // the cell of position p >= first with p % capacity == i
-  const unsigned long long p = first + ((unsigned long long)i + capacity - (first % capacity)) % capacity;
-  cell[i] = (unsigned long long)(uint32_t)p << 32;
-}
 
 #if defined(CNTMC_PROFILE_SEGMENTS)
 constexpr int kWarpTimeCols = 12;  // + cycles per loop segment of lane 0
@@ -301,12 +193,6 @@ struct KuboArgs {
   ClassLists          q;
   int32_t             hot_blocks;  // blocks [0, hot_blocks) serve the active classes first
   int32_t             fast_rounds; // events decided by the top entries of the site record, per iteration and lane (0 = off)
-  // two-engine kernel (kubo_engines_kernel): hand-over queues and the cursors of the excitons waiting in them
-  int32_t             refill_min;          // idle lanes that make a warp fetch new excitons
-  int32_t             park_min, park_max;  // flight warps: lanes with an event due that make the warp scatter; iterations a lane waits at most
-  Ring                ring[2];     // [0]: excitons waiting for a flight warp, [1]: for an event warp
-  unsigned long long* remaining;   // excitons that have not completed the launch yet
-  Cursors             cur;
   int64_t             P;
   double              dt;
   int32_t             nsteps;
@@ -482,271 +368,6 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
   }
 }
 
-
-// ---- K2, two-engine form -------------------------------------------------------------------------------------------------------
-// The same per-exciton arithmetic as kubo_kernel, scheduled so that the lanes of a warp run the same code.
-//
-// On the bench workload 97 % of the scattering events happen on a few "hot" sites, one after the other (tens of events
-// per time step), while 97 % of the excitons are in free flight and need one end-of-step operation per time step.
-// Which of the two an exciton needs changes inside a launch (a flight ends on a hot site; an exciton leaves one), and a
-// warp that holds both kinds pays for both code paths in every iteration with one or two lanes active.  So warps are
-// specialised and excitons change hands:
-//   * a FLIGHT warp ends time steps (chain walk, last leg, displacement, removal box, staging record).  The rare events
-//     of its excitons are gathered and run for several lanes at once; an exciton that scatters onto a hot site is
-//     handed over -- state and cursor to memory, index to ring[1] -- and the lane takes another.
-//   * an EVENT warp scatters: a few rounds of fast_event (decided by the site record, straight-line code), then the
-//     ordinary event path for what is left, and the step ends of its own excitons.  An exciton that ends a step on a
-//     quiet site with no event due within the next step goes back through ring[0].
-// A warp refills its lanes from its engine's queue and the launch's class lists; a warp that has run empty joins the
-// engine that has work, and leaves when every exciton has completed the launch (`remaining`).  Results cannot depend on
-// any of this: an exciton's trajectory is a function of its own state and stream, and the ensemble sums are reduced
-// from the (step, exciton) records in a fixed order.
-template <typename Draws, int kMinBlocks, bool kInstr>
-__global__ void __launch_bounds__(128, kMinBlocks) kubo_engines_kernel(const KuboArgs a) {
-  __shared__ double s_delta[3][128], s_old[3][128];
-  const int      tid = threadIdx.x, lane = threadIdx.x & 31;
-  const bool     fast_path = a.fast_rounds > 0;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  uint32_t       e = 0;
-  Lane           L{};
-  Draws          D{};
-  double         dt_rem = 0.0;
-  int32_t        step = 0;
-  uint32_t       ev0 = 0;
-  int32_t*       trace = nullptr;
-  int32_t        trace_base = 0;
-  bool           ok = true;
-  unsigned long long t_enter = 0, it_busy = 0, it_idle = 0;
-  int                iter = 0;
-  if (kInstr) t_enter = global_ns();
-  // instrumented build: time of lane 0 per phase {refill, step ends, fast events, ordinary events, hand-over, waiting}
-  unsigned long long ph_t = kInstr ? global_ns() : 0ULL, ph_ns[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}, ph_it[2] = {0, 0};
-  auto mark = [&](int v, int k) {
-    if (kInstr) {
-      const unsigned long long now = global_ns();
-      ph_ns[v][k] += now - ph_t;
-      ph_t = now;
-    }
-  };
-
-  auto start = [&](bool resumed, bool event_engine) {
-    const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject, nf = L.nfast;
-    load_lane<true>(L, a.S, a.T, (int64_t)e);
-    L.ncross = nc;
-    L.nprobe = np;
-    L.nreinject = nr;
-    L.nfast = nf;
-    init_draws(D, a.draws, a.S, (int64_t)e);
-    s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
-    if (resumed) {
-      step = __ldcg(a.cur.step + e);
-      dt_rem = __ldcg(a.cur.dt_rem + e);
-      s_old[0][tid] = __ldcg(a.cur.ox + e); s_old[1][tid] = __ldcg(a.cur.oy + e); s_old[2][tid] = __ldcg(a.cur.oz + e);
-      ev0 = 0u - __ldcg(a.cur.ev + e);  // L.nevent restarts at 0: nevent - ev0 keeps counting the events of the step
-    } else {
-      step = 0;
-      dt_rem = a.dt;
-      ev0 = 0;
-      s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;  // _old_pos = _pos (particle.cpp:59)
-    }
-    if (event_engine && fast_path && L.at_site) {  // fetch the rate fields now: the next event can take the fast path
-      (void)hop_info(L, a.T);
-      prefetch_l1(a.T.top + L.site);
-    }
-    if (kInstr && a.trace_sites) {  // the trace continues where the previous owner stopped
-      trace_base = __ldcg(a.trace_counts + e);
-      trace = a.trace_sites + (int64_t)e * a.trace_cap + trace_base;
-    }
-  };
-
-  const bool dedicated = (int)blockIdx.x < a.hot_blocks;  // these blocks stay with the event engine: arrivals find a warp
-  bool       role_v = dedicated;                          // event engine?
-  bool       have = false;
-  bool       try_fill = true;
-  bool       f_lists_dry = false, v_lists_dry = false;  // the launch's class lists never refill once they are empty
-  int        polls = 0, idle_polls = 0, park_age = 0;
-  for (;;) {
-    // ---- refill: migrated excitons of this engine first, then the launch's class lists
-    // (a refill is a chain of trips to memory -- queue counters, list, exciton state, site records -- that the whole warp
-    // waits for: it is worth it for several idle lanes at once, or when nothing else is left to do)
-    const unsigned idle_m = __ballot_sync(kFullMask, !have);
-    if (try_fill && idle_m && (__popc(idle_m) >= a.refill_min || (iter & 15) == 0 || idle_m == kFullMask)) {
-      try_fill = false;
-      uint32_t   e_new = 0;
-      const bool from_ring = ring_pop(a.ring[role_v ? 1 : 0], !have, lane, lt_mask, e_new, ok);
-      int64_t    e64 = 0;
-      bool       from_list = false;
-      if (!(role_v ? v_lists_dry : f_lists_dry)) {
-        from_list = take_exciton(a.q, !have && !from_ring, role_v, lane, lt_mask, e64);
-        if (__any_sync(kFullMask, !have && !from_ring && !from_list)) {
-          if (role_v) v_lists_dry = true; else f_lists_dry = true;
-        }
-      }
-      if (from_ring || from_list) {
-        e = from_ring ? e_new : (uint32_t)e64;
-        start(from_ring, role_v);
-        have = true;
-      }
-    }
-    mark(role_v, 0);
-    if (!__any_sync(kFullMask, have)) {
-      // the warp is empty: join the engine that has work, leave when the launch is complete
-      // (every counter sits on its own 128-byte line and idle warps back off: thousands of them may be polling)
-      bool v_work = false, f_work = false, all_done = false;
-      if (lane == 0) {
-        v_work = !v_lists_dry || ring_has_work(a.ring[1]);
-        f_work = !f_lists_dry || ring_has_work(a.ring[0]);
-        all_done = ld_relaxed_u64(a.remaining) == 0ULL;
-      }
-      v_work = __shfl_sync(kFullMask, v_work, 0);
-      f_work = __shfl_sync(kFullMask, f_work, 0);
-      all_done = __shfl_sync(kFullMask, all_done, 0);
-      try_fill = true;
-      if (role_v ? v_work : f_work) {
-        idle_polls = 0;
-        continue;
-      }
-      if ((role_v ? f_work : v_work) && !(dedicated && role_v)) {
-        role_v = !role_v;
-        idle_polls = 0;
-        continue;
-      }
-      if (all_done || !ok) break;
-      if (++polls > (1 << 18)) {  // seconds: something is lost; report instead of hanging
-        ok = false;
-        break;
-      }
-      __nanosleep(idle_polls < 4 ? (2000u << idle_polls) : 32000u);
-      ++idle_polls;
-      mark(role_v, 5);
-      continue;
-    }
-    if (kInstr) {
-      if (have) ++it_busy; else ++it_idle;
-      ++iter;
-    }
-    if ((iter & 15) == 0) try_fill = true;  // idle lanes look for new arrivals every few iterations
-    if (!kInstr) ++iter;
-    if (kInstr) ++ph_it[role_v];
-
-    bool finished = false, handoff = false;
-    // ---- end of a time step, for the lanes whose flight outlasts it (both engines)
-    if (have && !(L.ff <= dt_rem)) {  // particle.cpp:62 false
-      const double t = dt_rem;
-      const Leg    leg = fly(L, a.T, t, true);
-      L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
-      after_flight_step_end(L, a.T, D, leg, t, s_old[0][tid], s_old[1][tid], s_old[2][tid]);
-      double2* rec = reinterpret_cast<double2*>(a.stage + ((size_t)step * (size_t)a.P + (size_t)e));
-      __stcs(rec, make_double2(L.dx * L.dx, L.dy * L.dy));  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
-      __stcs(rec + 1, make_double2(L.dz * L.dz, (double)(L.nevent - ev0)));
-      s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
-      s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;
-      ++step;
-      dt_rem = a.dt;
-      ev0 = L.nevent;
-      finished = (step >= a.nsteps);
-      // an exciton that went quiet leaves the event engine: nothing due within the next step, and not on a hot site
-      if (role_v && !finished && L.ff > a.dt && hop_info(L, a.T).total * a.dt < 1.0) handoff = true;
-    }
-    mark(role_v, 1);
-    if (role_v) {
-      // ---- events decided by the site record: a few rounds of short straight-line code for the lanes that can
-      for (int k = 1; k < a.fast_rounds; ++k) {  // (fast_rounds = 1: the top entries are only consulted inside the ordinary event path)
-        bool did = false;
-        if (have && !finished && !handoff && (L.ff <= dt_rem))
-          did = fast_event(L, a.T, D, dt_rem, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u);
-        if (!__any_sync(kFullMask, did)) break;
-      }
-      mark(role_v, 2);
-      // ---- the ordinary event path for what is left
-      if (have && !finished && !handoff && (L.ff <= dt_rem)) {
-        const double t = L.ff;
-        const Leg    leg = fly(L, a.T, t, false);
-        dt_rem -= t;  // particle.cpp:63
-        after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u, fast_path);
-      }
-    } else {
-      // A flight warp scatters rarely (its excitons sit on quiet sites: an event every fifty steps or so).  Lanes with
-      // an event due wait until a few of them have gathered, so that the event path runs once for several lanes
-      // instead of in every other iteration for one; an exciton whose event lands it on a hot site changes engine.
-      const bool     due = have && !finished && (L.ff <= dt_rem);
-      const unsigned dm = __ballot_sync(kFullMask, due);
-      if (dm) {
-        const unsigned busy = __ballot_sync(kFullMask, have && !finished && !due);
-        if (__popc(dm) >= a.park_min || park_age >= a.park_max || busy == 0u) {
-          park_age = 0;
-          if (due) {
-            const double t = L.ff;
-            const Leg    leg = fly(L, a.T, t, false);
-            dt_rem -= t;  // particle.cpp:63
-            after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u);
-            if (hop_info(L, a.T).total * a.dt >= 1.0) handoff = true;
-          }
-        } else {
-          ++park_age;
-        }
-      }
-    }
-
-    mark(role_v, 3);
-    // ---- lanes that give their exciton up: it completed the launch, or it changes engine
-    const bool leave = have && (finished || handoff || L.stuck);
-    if (__any_sync(kFullMask, leave)) {
-      int cls = 0;
-      const bool done = leave && !(handoff && !L.stuck);
-      if (leave) {
-        materialize(L, a.T);
-        L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
-        store_lane(L, a.S, (int64_t)e);
-        if (kInstr && a.trace_counts) __stcg(a.trace_counts + e, trace_base + (int32_t)L.nevent);
-        if (done) {
-          cls = activity_class(hop_info(L, a.T).total * a.dt);
-          if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
-          if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
-        } else {
-          __stcg(a.cur.step + e, step);
-          __stcg(a.cur.dt_rem + e, dt_rem);
-          __stcg(a.cur.ox + e, s_old[0][tid]); __stcg(a.cur.oy + e, s_old[1][tid]); __stcg(a.cur.oz + e, s_old[2][tid]);
-          __stcg(a.cur.ev + e, L.nevent - ev0);
-        }
-      }
-      file_excitons(a.q, done, cls, e, lane, lt_mask);
-      if (!ring_push(a.ring[role_v ? 0 : 1], leave && !done, e, lane, lt_mask)) ok = false;
-      const unsigned nd = __ballot_sync(kFullMask, done);
-      if (nd && lane == 0) atomicAdd(a.remaining, 0ULL - (unsigned long long)__popc(nd));
-      if (leave) have = false;
-      try_fill = true;
-    }
-    mark(role_v, 4);
-  }
-  if (!ok) atomicOr(a.flags + FLAG_STUCK, 1);
-  if (kInstr && lane == 0) {
-    for (int v = 0; v < 2; ++v) {
-      for (int k = 0; k < 6; ++k) atomicAdd(a.counters + CTR_PHASE + 6 * v + k, ph_ns[v][k]);
-      atomicAdd(a.counters + CTR_ITER + v, ph_it[v]);
-    }
-  }
-
-  const unsigned nr = __reduce_add_sync(kFullMask, L.nreinject);
-  if (lane == 0 && nr) atomicAdd(a.counters + CTR_REINJECT, (unsigned long long)nr);
-  if (kInstr) {
-    const unsigned nc = __reduce_add_sync(kFullMask, L.ncross);
-    const unsigned np = __reduce_add_sync(kFullMask, L.nprobe);
-    const unsigned nf = __reduce_add_sync(kFullMask, L.nfast);
-    const unsigned long long t_exit = global_ns();
-    atomicAdd(a.counters + CTR_LANE_BUSY, it_busy);
-    atomicAdd(a.counters + CTR_LANE_IDLE, it_idle);
-    if (lane == 0) {
-      if (nc) atomicAdd(a.counters + CTR_CROSS, (unsigned long long)nc);
-      if (np) atomicAdd(a.counters + CTR_PROBE, (unsigned long long)np);
-      if (nf) atomicAdd(a.counters + CTR_FAST, (unsigned long long)nf);
-      atomicAdd(a.counters + CTR_WARP_NS, t_exit - t_enter);
-      atomicMax(a.counters + CTR_T_FIRST_INV, ~t_enter);
-      atomicMax(a.counters + CTR_T_LAST, t_exit);
-      atomicAdd(a.counters + CTR_WARPS, 1ULL);
-    }
-  }
-}
 
 // file every exciton under its activity class (first launch after creation or after an upload of the population)
 __global__ void __launch_bounds__(256) classify_kernel(const Tables T, const int32_t* site, int64_t P, double dt, ClassLists q) {

@@ -109,7 +109,7 @@ def test_chunking_sorting_and_occupancy_do_not_change_results():
                  dict(chunk_steps=200, sort=1, occupancy=5), dict(chunk_steps=64, sort=1, stage_mb=1), dict(chunk_steps=8, hot_pct=0),
                  dict(chunk_steps=3, hot_pct=100), dict(chunk_steps=8, hot_pct=30, occupancy=6),
                  dict(fast_rounds=0), dict(fast_rounds=1, chunk_steps=16), dict(fast_rounds=32, hot_pct=50),
-                 dict(engines=0), dict(engines=0, fast_rounds=0, chunk_steps=9), dict(engines=1, hot_pct=5, chunk_steps=33)):
+                 dict(fast_rounds=4, chunk_steps=9), dict(fast_rounds=2, hot_pct=5, chunk_steps=33)):
         e = Engine(mc)
         e.set_mesh(pos, ori)
         for k, v in opts.items():
