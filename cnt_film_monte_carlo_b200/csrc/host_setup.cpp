@@ -2,6 +2,8 @@
 // (the reference's x86-64 baseline build has none), which keeps the rate table and the domain arithmetic bit-identical.
 #include "host_setup.h"
 
+#include <limits>
+#include <cstring>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -482,5 +484,16 @@ std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vec
     r.spare = 0.0;
   }
   return rec;
+}
+
+std::vector<double> make_segment_times(const std::vector<SiteRec>& rec) {
+  const size_t        N = rec.size();
+  const double        nan = std::numeric_limits<double>::quiet_NaN();
+  std::vector<double> seg(N + 2 * kSegPad, nan);
+  for (size_t s = 0; s + 1 < N; ++s) {
+    const SiteRec &a = rec[s], &b = rec[s + 1];
+    if (a.right == (int32_t)(s + 1) && b.left == (int32_t)s && memcmp(&a.q_right, &b.q_left, sizeof(double)) == 0) seg[kSegPad + s] = a.q_right;
+  }
+  return seg;
 }
 }  // namespace cntmc

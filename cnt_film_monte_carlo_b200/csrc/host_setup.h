@@ -99,4 +99,8 @@ namespace cntmc {
 // links and the two segment flight times of every site (hop_core.h SiteRec) plus the position records; the rate fields
 // (total, 1/total, CSR row) are filled by the neighbour-table kernel.
 std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vector<PosRec>& pos);
+// Tables::seg with its padding: element 4 + s is the segment time between sites s and s+1 where right[s] == s+1 and
+// left[s+1] == s (and both records hold the same time, bit for bit), NaN elsewhere; four NaNs on either side
+constexpr int kSegPad = 4;
+std::vector<double> make_segment_times(const std::vector<SiteRec>& rec);
 }  // namespace cntmc

@@ -133,6 +133,11 @@ class Emul:
         self.L.emul_set_fast_path.argtypes = [C.c_void_p, C.c_int]
         self.L.emul_set_fast_path(self.h, 1 if on else 0)
 
+    def set_runs(self, on=True):
+        """chain walks over memory-consecutive sites on segment times (hop_core.h fly) vs record by record"""
+        self.L.emul_set_runs.argtypes = [C.c_void_p, C.c_int]
+        self.L.emul_set_runs(self.h, 1 if on else 0)
+
     def particles(self):
         P = self.P
         site, heading, ndraw = np.empty(P, np.int32), np.empty(P, np.int32), np.empty(P, np.uint32)

@@ -23,6 +23,8 @@ struct Emul {
   Injection            inj;
   std::vector<SiteRec> site;
   std::vector<TopRec>  top;
+  std::vector<double>  seg;
+  bool                 runs = true;
   std::vector<PosRec>  pos;
   std::vector<double>  cum;
   std::vector<int32_t> nbr;
@@ -127,6 +129,8 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
       e->guards += guard;
     }
     e->T.top = e->top.data();
+    e->seg = make_segment_times(e->site);
+    e->T.seg = e->runs ? e->seg.data() + kSegPad : nullptr;
     e->T.site = e->site.data();
     e->T.pos = e->pos.data();
     e->row.resize(e->cum.size());
@@ -256,6 +260,10 @@ int emul_kubo_step(Emul* e, double dt, int64_t nsteps, double* msd, int trace_ca
 int64_t emul_hops(Emul* e) { return e->hops; }
 int64_t emul_fast_events(Emul* e) { return e->fast; }
 void emul_set_fast_path(Emul* e, int on) { e->fast_path = on != 0; }
+void emul_set_runs(Emul* e, int on) {
+  e->runs = on != 0;
+  e->T.seg = e->runs && !e->seg.empty() ? e->seg.data() + kSegPad : nullptr;
+}
 void emul_particles(Emul* e, int32_t* site, double* pos, double* delta, double* ff, int32_t* heading, uint32_t* ndraw) {
   const size_t P = e->lanes.size();
   for (size_t i = 0; i < P; ++i) {

@@ -140,6 +140,26 @@ def test_fast_event_path_is_bit_identical_and_matches_oracle(golden):
     assert np.array_equal(np.diff(off_t)[500:], np.diff(ob)) and np.array_equal(flat_t, fb)
 
 
+def test_chain_walks_on_segment_times_are_bit_identical(golden):
+    """fly() over runs of memory-consecutive sites (Tables::seg) against the record-by-record walk: a film whose tubes
+    are cut by the trim box (permuted site order, broken runs, reflections at chain ends) and the golden film."""
+    pos, ori = film.film(NT=120, NP=80, a=5.0, LX=300.0, LY=60.0, seed=3)
+    mc = dict(base_mc())
+    mc["trim limits"] = {"xlim": [2e-8, 2.6e-7], "ylim": [0.0, 5e-8], "zlim": [1e-8, 2.8e-7]}
+    for m, p, o, dt in ((mc, pos, ori, 1e-13), (golden.mc, golden.pos_nm, golden.orient, golden.dt), (mc, pos, ori, 7e-13)):
+        res = []
+        for on in (False, True):
+            e = Emul(m)
+            e.kubo_init(p, o)
+            e.set_runs(on)
+            e.create_philox(300, seed=5)
+            msd = e.kubo_step(dt, 120, trace_cap=1 << 12)
+            res.append((e.particles(), msd, e.trace(), e.hops()))
+        (pa, ma, (oa, fa), ha), (pb, mb, (ob, fb), hb) = res
+        assert all(np.array_equal(pa[k], pb[k]) for k in pa) and np.array_equal(ma, mb)
+        assert np.array_equal(oa, ob) and np.array_equal(fa, fb) and ha == hb and ha > 300
+
+
 def test_guided_search_equals_reference_loop_for_every_bucket():
     e = Emul(base_mc())
     rng = np.random.default_rng(5)
