@@ -144,6 +144,7 @@ struct cntmc_handle {
   DevBuf<SiteRec> d_site;
   DevBuf<TopRec> d_top;
   DevBuf<double> d_seg;
+  DevBuf<DirRec> d_dir;
   DevBuf<PosRec>  d_pos;
   DevBuf<RowEntry> d_row;
   DevBuf<int32_t>  d_inject, d_c1, d_c2;
@@ -183,6 +184,7 @@ struct cntmc_handle {
   // tuning
   int64_t opt_chunk = 64;     // time steps per launch
   int64_t opt_sort = 1;       // (kept for compatibility; activity classes replaced the sort)
+  int64_t opt_dirs = 1;         // last legs that leave from a site use stored unit vectors
   int64_t opt_runs = 1;         // chain walks over memory-consecutive sites read segment times instead of chasing records
   int64_t opt_fast_rounds = 1;  // 0: row search only; 1: the row's three widest entries are tried first; n > 1: plus n-1 rounds of fast_event per iteration
   int64_t opt_hot_pct = 30;   // share of the blocks that serve the most active classes first
@@ -331,6 +333,7 @@ void common_init(cntmc_t* h) {
   h->d_site.upload(rec, st);
   h->d_top.alloc((size_t)N);
   h->d_seg.upload(make_segment_times(rec), st);
+  h->d_dir.upload(make_direction_records(rec, posrec), st);
   h->d_pos.upload(posrec, st);
 
   CsrArgs a{};
@@ -395,6 +398,7 @@ void common_init(cntmc_t* h) {
   h->T.site = h->d_site.p;
   h->T.top = h->d_top.p;
   h->T.seg = h->opt_runs ? h->d_seg.p + kSegPad : nullptr;
+  h->T.dir = h->opt_dirs ? h->d_dir.p : nullptr;
   h->T.pos = h->d_pos.p;
   h->T.row = h->d_row.p;
   h->T.velocity = h->prm.velocity;
@@ -1252,6 +1256,9 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "occupancy") {
       require(value >= 4 && value <= 8, "occupancy must be 4 to 8 blocks per SM");
       h->opt_occupancy = value;
+    } else if (k == "dirs") {
+      h->opt_dirs = value ? 1 : 0;
+      if (h->initialised) h->T.dir = h->opt_dirs ? h->d_dir.p : nullptr;
     } else if (k == "runs") {
       h->opt_runs = value ? 1 : 0;
       if (h->initialised) h->T.seg = h->opt_runs ? h->d_seg.p + kSegPad : nullptr;
@@ -1279,6 +1286,7 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "hot_pct") return h->opt_hot_pct;
   if (k == "fast_rounds") return h->opt_fast_rounds;
   if (k == "runs") return h->opt_runs;
+  if (k == "dirs") return h->opt_dirs;
   if (k == "stage_mb") return h->opt_stage_mb;
   if (k.rfind("dbg_", 0) == 0) {  // raw device counters of the last instrumented hop-kernel launch (option "stats")
     unsigned long long ctrs[CTR_COUNT];

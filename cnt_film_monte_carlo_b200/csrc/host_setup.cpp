@@ -486,6 +486,25 @@ std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vec
   return rec;
 }
 
+// normalise(next.pos - pos) with the arithmetic of move_along (hop_core.h): w / (|w| > 0 ? |w| : 1)
+std::vector<DirRec> make_direction_records(const std::vector<SiteRec>& rec, const std::vector<PosRec>& pos) {
+  std::vector<DirRec> dir(rec.size(), DirRec{0, 0, 0, 0, 0, 0, 0, 0});
+  for (size_t i = 0; i < rec.size(); ++i) {
+    for (int side = 0; side < 2; ++side) {
+      const int32_t n = side == 0 ? rec[i].right : rec[i].left;
+      if (n < 0) continue;
+      const double wx = pos[(size_t)n].x - pos[i].x, wy = pos[(size_t)n].y - pos[i].y, wz = pos[(size_t)n].z - pos[i].z;
+      const double nn = norm3(wx, wy, wz);
+      const double den = (nn > 0) ? nn : 1.0;
+      double*      u = side == 0 ? &dir[i].rx : &dir[i].lx;
+      u[0] = wx / den;
+      u[1] = wy / den;
+      u[2] = wz / den;
+    }
+  }
+  return dir;
+}
+
 std::vector<double> make_segment_times(const std::vector<SiteRec>& rec) {
   const size_t        N = rec.size();
   const double        nan = std::numeric_limits<double>::quiet_NaN();

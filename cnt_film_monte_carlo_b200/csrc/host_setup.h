@@ -101,6 +101,7 @@ namespace cntmc {
 std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vector<PosRec>& pos);
 // Tables::seg with its padding: element 4 + s is the segment time between sites s and s+1 where right[s] == s+1 and
 // left[s+1] == s (and both records hold the same time, bit for bit), NaN elsewhere; four NaNs on either side
+std::vector<DirRec> make_direction_records(const std::vector<SiteRec>& rec, const std::vector<PosRec>& pos);
 constexpr int kSegPad = 4;
 std::vector<double> make_segment_times(const std::vector<SiteRec>& rec);
 }  // namespace cntmc

@@ -24,6 +24,7 @@ struct Emul {
   std::vector<SiteRec> site;
   std::vector<TopRec>  top;
   std::vector<double>  seg;
+  std::vector<DirRec>  dir;
   bool                 runs = true;
   std::vector<PosRec>  pos;
   std::vector<double>  cum;
@@ -131,6 +132,8 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
     e->T.top = e->top.data();
     e->seg = make_segment_times(e->site);
     e->T.seg = e->runs ? e->seg.data() + kSegPad : nullptr;
+    e->dir = make_direction_records(e->site, e->pos);
+    e->T.dir = e->runs ? e->dir.data() : nullptr;
     e->T.site = e->site.data();
     e->T.pos = e->pos.data();
     e->row.resize(e->cum.size());
@@ -263,6 +266,7 @@ void emul_set_fast_path(Emul* e, int on) { e->fast_path = on != 0; }
 void emul_set_runs(Emul* e, int on) {
   e->runs = on != 0;
   e->T.seg = e->runs && !e->seg.empty() ? e->seg.data() + kSegPad : nullptr;
+  e->T.dir = e->runs && !e->dir.empty() ? e->dir.data() : nullptr;
 }
 void emul_particles(Emul* e, int32_t* site, double* pos, double* delta, double* ff, int32_t* heading, uint32_t* ndraw) {
   const size_t P = e->lanes.size();
