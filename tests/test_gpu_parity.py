@@ -127,6 +127,41 @@ def test_chunking_sorting_and_occupancy_do_not_change_results():
     assert hops > 5000
 
 
+def test_shortcuts_do_not_change_results_on_a_trimmed_film():
+    """Top entries, segment-time chain walks and stored directions against the plain paths, and all of them against the
+    oracle, on a film whose tubes are cut by the trim box (permuted site order, broken runs, reflections at chain ends)."""
+    pos, ori = film.film(NT=120, NP=80, a=5.0, LX=300.0, LY=60.0, seed=3)
+    mc = base_mc(**{"trim limits": {"xlim": [2e-8, 2.6e-7], "ylim": [0.0, 5e-8], "zlim": [1e-8, 2.8e-7]}})
+    res = []
+    for opts in (dict(fast_rounds=0, runs=0, dirs=0), dict(fast_rounds=1, runs=1, dirs=1), dict(fast_rounds=3, runs=1, dirs=0),
+                 dict(fast_rounds=0, runs=0, dirs=1), dict(fast_rounds=1, runs=1, dirs=1, chunk_steps=5)):
+        e = Engine(mc)
+        e.set_mesh(pos, ori)
+        for k, v in opts.items():
+            e.set_option(k, v)
+        e.kubo_init()
+        e.kubo_create_particles(3000, seed=11)
+        e.trace_enable(1 << 11)
+        msd = np.concatenate([e.kubo_step(1e-13, 70), e.kubo_step(7e-13, 30)])
+        counts, sites = e.trace()
+        assert counts.max() < (1 << 11)
+        flat = np.concatenate([sites[i, :counts[i]] for i in range(len(counts))])
+        res.append((e.particles(), msd, counts, flat, e.hops(), e.reinjections()))
+    for r in res[1:]:
+        assert all(np.array_equal(r[0][k], res[0][0][k]) for k in r[0])
+        assert np.array_equal(r[1], res[0][1]) and np.array_equal(r[2], res[0][2]) and r[4:] == res[0][4:]
+        assert np.array_equal(r[3], res[0][3])
+    t = T1m.T1()
+    t.kubo_init(mc, pos, ori)
+    t.draws_philox(11)
+    t.create_particles(3000)
+    t.kubo_step(1e-13, 70, want_msd=False)
+    t.kubo_step(7e-13, 30, want_msd=False)
+    pt, pe = t.particles(), res[1][0]
+    assert np.array_equal(pe["site"], pt["site"]) and np.array_equal(pe["heading"], pt["heading"].astype(np.uint8))
+    assert np.allclose(pe["pos"], pt["pos"], rtol=1e-9, atol=1e-18) and res[1][4] == t.hops() and res[1][5] == t.reinjections()
+
+
 def test_host_state_call_equals_resident_call(golden_small):
     g = golden_small
     a, b = engine_for(g), engine_for(g)
