@@ -220,7 +220,7 @@ def run_ours(args, rank, world, local_rank):
     pos, ori = film.film(**film.CONFIG_FILMS["C2"])
     eng = Engine(mc_block(P), device=local_rank, stream=stream.cuda_stream)
     eng.set_mesh(pos, ori)
-    for k, v in (("chunk_steps", args.chunk), ("hot_pct", args.hot_pct), ("occupancy", args.occupancy), ("fast_rounds", args.fast_rounds)):
+    for k, v in (("chunk_steps", args.chunk), ("hot_pct", args.hot_pct), ("occupancy", args.occupancy), ("top_entries", args.top_entries)):
         eng.set_option(k, v)
     for kv in args.opt:                               # any other engine option, name=value
         k, v = kv.split("=")
@@ -379,7 +379,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=64, help="time steps per kernel launch")
     ap.add_argument("--hot-pct", type=int, default=30, help="share of blocks serving the most active excitons first")
     ap.add_argument("--opt", action="append", default=[], help="extra engine option name=value (repeatable)")
-    ap.add_argument("--fast-rounds", type=int, default=1, help="0: row search only, 1: the three widest row entries first, n>1: plus n-1 fast-event rounds per iteration")
+    ap.add_argument("--top-entries", type=int, default=1, help="1: the three widest entries of a row are tried before the row is searched")
     ap.add_argument("--occupancy", type=int, default=5, help="resident 128-thread blocks per SM of the hop kernel (4, 5, 6, 8)")
     ap.add_argument("--stage-mb", type=int, default=0, help="cap on the (step, exciton) staging buffer in MiB (0 = engine default)")
     ap.add_argument("--e2e-steps", type=int, default=5)

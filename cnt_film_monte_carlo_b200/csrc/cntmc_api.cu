@@ -186,7 +186,7 @@ struct cntmc_handle {
   int64_t opt_sort = 1;       // (kept for compatibility; activity classes replaced the sort)
   int64_t opt_dirs = 1;         // last legs that leave from a site use stored unit vectors
   int64_t opt_runs = 1;         // chain walks over memory-consecutive sites read segment times instead of chasing records
-  int64_t opt_fast_rounds = 1;  // 0: row search only; 1: the row's three widest entries are tried first; n > 1: plus n-1 rounds of fast_event per iteration
+  int64_t opt_top_entries = 1;  // the three widest entries of a row are tried before the row is searched
   int64_t opt_hot_pct = 30;   // share of the blocks that serve the most active classes first
   int64_t opt_block = 128;  // threads per block of the hop kernel
   int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
@@ -544,7 +544,7 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     a.draws = h->draws;
     a.q = lists(h->cur_list);
     a.hot_blocks = (int32_t)((int64_t)grid * h->opt_hot_pct / 100);
-    a.fast_rounds = (int32_t)h->opt_fast_rounds;
+    a.top_entries = (int32_t)h->opt_top_entries;
     a.P = h->P;
     a.dt = dt;
     a.nsteps = n;
@@ -951,7 +951,7 @@ static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned 
     a.dt = dt;
     a.nsteps = n;
     a.n_seg = h->n_seg;
-    a.use_top = h->opt_fast_rounds > 0 ? 1 : 0;
+    a.use_top = h->opt_top_entries ? 1 : 0;
     a.ymin = h->dom.lo[1];
     a.ymax = h->dom.hi[1];
     a.dy = (h->dom.hi[1] - h->dom.lo[1]) / double(h->n_seg);  // monte_carlo.h:446
@@ -1262,9 +1262,8 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "runs") {
       h->opt_runs = value ? 1 : 0;
       if (h->initialised) h->T.seg = h->opt_runs ? h->d_seg.p + kSegPad : nullptr;
-    } else if (k == "fast_rounds") {
-      require(value >= 0 && value <= 64, "fast_rounds must be in [0, 64]");
-      h->opt_fast_rounds = value;
+    } else if (k == "top_entries") {
+      h->opt_top_entries = value ? 1 : 0;
     } else if (k == "stage_mb") {
       require(value >= 0, "stage_mb must not be negative (0 = a third of the free device memory)");
       h->opt_stage_mb = value;
@@ -1284,7 +1283,7 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "block") return h->opt_block;
   if (k == "occupancy") return h->opt_occupancy;
   if (k == "hot_pct") return h->opt_hot_pct;
-  if (k == "fast_rounds") return h->opt_fast_rounds;
+  if (k == "top_entries") return h->opt_top_entries;
   if (k == "runs") return h->opt_runs;
   if (k == "dirs") return h->opt_dirs;
   if (k == "stage_mb") return h->opt_stage_mb;
@@ -1296,7 +1295,7 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
     if (k == "dbg_warps") return (int64_t)ctrs[CTR_WARPS];
     if (k == "dbg_lane_busy") return (int64_t)ctrs[CTR_LANE_BUSY];
     if (k == "dbg_lane_idle") return (int64_t)ctrs[CTR_LANE_IDLE];
-    if (k == "dbg_fast_events") return (int64_t)ctrs[CTR_FAST];
+    if (k == "dbg_top_events") return (int64_t)ctrs[CTR_FAST];
   }
   return -1;
 }

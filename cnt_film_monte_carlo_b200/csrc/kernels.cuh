@@ -26,7 +26,7 @@ struct ExcitonArrays {
   int32_t*  site;          // particle::_scat_ptr
   uint8_t*  heading;       // particle::_heading_right
   uint32_t* ndraw;         // next draw index of the exciton's stream
-  uint32_t* last_events;   // events in the previous launch (load-balancing key)
+  uint32_t* last_events;   // (unused since the activity classes; kept in the layout of uploads / compaction)
   uint64_t* gid;           // stream id where excitons are created and destroyed (contact mode); null = first_gid + index
 };
 
@@ -64,7 +64,6 @@ __device__ __forceinline__ void store_lane(const Lane& L, const ExcitonArrays& S
   __stcs(S.site + e, L.site);
   __stcs(S.heading + e, (uint8_t)(L.heading_right ? 1 : 0));
   __stcs(S.ndraw + e, L.ndraw);
-  __stcs(S.last_events + e, L.nevent);
 }
 
 template <typename Draws>
@@ -192,7 +191,7 @@ struct KuboArgs {
   DrawConfig          draws;
   ClassLists          q;
   int32_t             hot_blocks;  // blocks [0, hot_blocks) serve the active classes first
-  int32_t             fast_rounds; // events decided by the top entries of the site record, per iteration and lane (0 = off)
+  int32_t             top_entries; // try the three widest entries of a row before searching it
   int64_t             P;
   double              dt;
   int32_t             nsteps;
@@ -221,7 +220,6 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
   // they live in shared memory (one slot per thread) so that the event path does not carry 12 registers of them.
   __shared__ double s_delta[3][128], s_old[3][128];
   const int      tid = threadIdx.x, lane = threadIdx.x & 31;
-  const bool     fast_path = a.fast_rounds > 0;
   const unsigned lt_mask = (1u << lane) - 1u;
   const bool     hot_role = (int)blockIdx.x < a.hot_blocks;
   uint32_t       e = 0;
@@ -229,9 +227,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
   Draws          D{};
   double         dt_rem = 0.0;
   int32_t        step = 0;
-  uint32_t       ev0 = 0;
   int32_t*       trace = nullptr;
-  int32_t        trace_base = 0;
+  int32_t        trace_base = 0;  // events already in the exciton's trace when the current time step began
   unsigned long long t_enter = 0, it_busy = 0, it_idle = 0, t_dry = 0;
   int                iter = 0;
   if (kInstr) t_enter = global_ns();
@@ -249,7 +246,6 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
     init_draws(D, a.draws, a.S, (int64_t)e);
     step = 0;
     dt_rem = a.dt;
-    ev0 = 0;
     s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
     s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;  // _old_pos = _pos (particle.cpp:59)
     if (kInstr && a.trace_sites) {  // the trace continues where the previous launch stopped
@@ -286,29 +282,24 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
         // streaming stores: written once, read once by the reduction, must not evict the tables from L2
         double2* rec = reinterpret_cast<double2*>(a.stage + ((size_t)step * (size_t)a.P + (size_t)e));
         __stcs(rec, make_double2(L.dx * L.dx, L.dy * L.dy));  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
-        __stcs(rec + 1, make_double2(L.dz * L.dz, (double)(L.nevent - ev0)));
+        __stcs(rec + 1, make_double2(L.dz * L.dz, (double)L.nevent));  // events of this time step
         s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
         s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;
         ++step;
         dt_rem = a.dt;
-        ev0 = L.nevent;
+        if (kInstr) {
+          trace_base += (int32_t)L.nevent;
+          if (trace) trace += L.nevent;
+        }
+        L.nevent = 0;
         finished = (step >= a.nsteps);
       }
       CNTMC_SEG(L, 5);  // step-end path (own, or waiting for the lanes that run it)
-      // Events that the record of the exciton's site decides (fast_event): short straight-line code, one trip to
-      // memory, no search and no chain walk.  The lanes that can take it run a few rounds of it together; the other
-      // lanes wait, and whatever a lane cannot do this way is left to the ordinary event path below.
-      for (int k = 1; k < a.fast_rounds; ++k) {  // (fast_rounds = 1: the top entries are only consulted inside the ordinary event path)
-        bool did = false;
-        if (have && !finished && (L.ff <= dt_rem))
-          did = fast_event(L, a.T, D, dt_rem, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u);
-        if (!__any_sync(kFullMask, did)) break;
-      }
       if (have && !finished && (L.ff <= dt_rem)) {
         const double t = L.ff;
         const Leg    leg = fly(L, a.T, t, false);
         dt_rem -= t;  // particle.cpp:63
-        after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u, fast_path);
+        after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u, a.top_entries != 0);
       }
       CNTMC_SEG(L, 7);  // waiting for the other lanes of the warp to finish their events
       finished = have && (finished || L.stuck);

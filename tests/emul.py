@@ -37,7 +37,7 @@ class Emul:
         L.emul_error.argtypes = [V]
         L.emul_destroy.argtypes = [V]
         L.emul_kubo_init.argtypes = [V, I64, I64, V, V]
-        for n in ("emul_num_sites", "emul_nnz", "emul_guards", "emul_num_inject", "emul_hops", "emul_fast_events"):
+        for n in ("emul_num_sites", "emul_nnz", "emul_guards", "emul_num_inject", "emul_hops", "emul_top_events"):
             getattr(L, n).restype = I64
             getattr(L, n).argtypes = [V]
         L.emul_sites.argtypes = [V] * 7
@@ -125,13 +125,13 @@ class Emul:
     def hops(self):
         return self.L.emul_hops(self.h)
 
-    def fast_events(self):
-        """events decided by the top entries of the site record (hop_core.h fast_event)"""
-        return self.L.emul_fast_events(self.h)
+    def top_events(self):
+        """events decided by the top entries of the site record (hop_core.h after_flight_scatter)"""
+        return self.L.emul_top_events(self.h)
 
-    def set_fast_path(self, on=True):
-        self.L.emul_set_fast_path.argtypes = [C.c_void_p, C.c_int]
-        self.L.emul_set_fast_path(self.h, 1 if on else 0)
+    def set_top_entries(self, on=True):
+        self.L.emul_set_top_entries.argtypes = [C.c_void_p, C.c_int]
+        self.L.emul_set_top_entries(self.h, 1 if on else 0)
 
     def set_runs(self, on=True):
         """chain walks over memory-consecutive sites on segment times (hop_core.h fly) vs record by record"""

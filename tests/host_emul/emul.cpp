@@ -39,7 +39,7 @@ struct Emul {
   std::vector<double>  r_logs;
   bool                 replay = false;
   int64_t              guards = 0, hops = 0, fast = 0;
-  bool                 fast_path = false;  // decide events by the top entries of the site record where possible
+  bool                 use_top = false;  // decide events by the top entries of the site record where possible
   std::string          err;
   std::vector<std::vector<int32_t>> trace;
 };
@@ -239,7 +239,7 @@ static int step(Emul* e, double dt, int64_t nsteps, double* msd, int trace_cap) 
     c.step = 0;
     begin_step(c, L, dt);
     while (c.step < nsteps && !L.stuck) {
-      if (advance(L, e->T, D, c, trace_cap > 0 ? tr.data() : nullptr, (uint32_t)trace_cap, e->fast_path)) {
+      if (advance(L, e->T, D, c, trace_cap > 0 ? tr.data() : nullptr, (uint32_t)trace_cap, e->use_top)) {
         sums[c.step * 3 + 0] += L.dx * L.dx;
         sums[c.step * 3 + 1] += L.dy * L.dy;
         sums[c.step * 3 + 2] += L.dz * L.dz;
@@ -261,8 +261,8 @@ int emul_kubo_step(Emul* e, double dt, int64_t nsteps, double* msd, int trace_ca
   return e->replay ? step<ReplayDraws>(e, dt, nsteps, msd, trace_cap) : step<PhiloxDraws>(e, dt, nsteps, msd, trace_cap);
 }
 int64_t emul_hops(Emul* e) { return e->hops; }
-int64_t emul_fast_events(Emul* e) { return e->fast; }
-void emul_set_fast_path(Emul* e, int on) { e->fast_path = on != 0; }
+int64_t emul_top_events(Emul* e) { return e->fast; }
+void emul_set_top_entries(Emul* e, int on) { e->use_top = on != 0; }
 void emul_set_runs(Emul* e, int on) {
   e->runs = on != 0;
   e->T.seg = e->runs && !e->seg.empty() ? e->seg.data() + kSegPad : nullptr;
@@ -307,7 +307,7 @@ int64_t emul_select_guided(const double* cum, int64_t d, int32_t r) {
   guide_bracket(g[0], g[1], (uint32_t)d, r, lo, hi);
   return select_via_entries(cum, d, lo, hi, dice);
 }
-// the decision of fast_event: index of the top entry whose interval holds dice, or -1 (ordinary search needed)
+// the decision of the top entries (after_flight_scatter): index of the top entry whose interval holds dice, or -1 (ordinary search needed)
 int64_t emul_select_top(const double* cum, int64_t d, double dice) {
   TopEntries top;
   top.clear();

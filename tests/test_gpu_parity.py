@@ -108,8 +108,8 @@ def test_chunking_sorting_and_occupancy_do_not_change_results():
     for opts in (dict(chunk_steps=64, sort=1, occupancy=6), dict(chunk_steps=7, sort=0, occupancy=4), dict(chunk_steps=1, sort=1, occupancy=8),
                  dict(chunk_steps=200, sort=1, occupancy=5), dict(chunk_steps=64, sort=1, stage_mb=1), dict(chunk_steps=8, hot_pct=0),
                  dict(chunk_steps=3, hot_pct=100), dict(chunk_steps=8, hot_pct=30, occupancy=6),
-                 dict(fast_rounds=0), dict(fast_rounds=1, chunk_steps=16), dict(fast_rounds=32, hot_pct=50),
-                 dict(fast_rounds=4, chunk_steps=9), dict(fast_rounds=2, hot_pct=5, chunk_steps=33)):
+                 dict(top_entries=0), dict(top_entries=1, chunk_steps=16), dict(top_entries=0, runs=0, hot_pct=50),
+                 dict(dirs=0, chunk_steps=9), dict(runs=0, hot_pct=5, chunk_steps=33)):
         e = Engine(mc)
         e.set_mesh(pos, ori)
         for k, v in opts.items():
@@ -133,8 +133,8 @@ def test_shortcuts_do_not_change_results_on_a_trimmed_film():
     pos, ori = film.film(NT=120, NP=80, a=5.0, LX=300.0, LY=60.0, seed=3)
     mc = base_mc(**{"trim limits": {"xlim": [2e-8, 2.6e-7], "ylim": [0.0, 5e-8], "zlim": [1e-8, 2.8e-7]}})
     res = []
-    for opts in (dict(fast_rounds=0, runs=0, dirs=0), dict(fast_rounds=1, runs=1, dirs=1), dict(fast_rounds=3, runs=1, dirs=0),
-                 dict(fast_rounds=0, runs=0, dirs=1), dict(fast_rounds=1, runs=1, dirs=1, chunk_steps=5)):
+    for opts in (dict(top_entries=0, runs=0, dirs=0), dict(top_entries=1, runs=1, dirs=1), dict(top_entries=1, runs=1, dirs=0),
+                 dict(top_entries=0, runs=0, dirs=1), dict(top_entries=1, runs=1, dirs=1, chunk_steps=5)):
         e = Engine(mc)
         e.set_mesh(pos, ori)
         for k, v in opts.items():

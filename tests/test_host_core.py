@@ -93,7 +93,7 @@ def test_select_entry_equals_reference_loop():
 
 
 def test_top_entries_decide_exactly_what_the_reference_loop_decides():
-    """fast_event's shortcut: a dice inside the interval of one of the three widest entries selects that entry."""
+    """The shortcut of the event path: a dice inside the interval of one of the three widest entries selects that entry."""
     import ctypes
     e = Emul(base_mc())
     e.L.emul_select_top.restype = ctypes.c_int64
@@ -113,16 +113,16 @@ def test_top_entries_decide_exactly_what_the_reference_loop_decides():
     assert decided > 4000
 
 
-def test_fast_event_path_is_bit_identical_and_matches_oracle(golden):
-    """Events decided by the top entries of the site record (the kernel's fast loop) change nothing."""
+def test_top_entries_path_is_bit_identical_and_matches_oracle(golden):
+    """Events decided by the top entries of the row change nothing."""
     res = []
     for on in (False, True):
         e = Emul(golden.mc)
         e.kubo_init(golden.pos_nm, golden.orient)
-        e.set_fast_path(on)
+        e.set_top_entries(on)
         e.create_philox(96, seed=77, first_gid=500)
         msd = e.kubo_step(golden.dt, 150, trace_cap=1 << 14)
-        res.append((e.particles(), msd, e.trace(), e.hops(), e.fast_events()))
+        res.append((e.particles(), msd, e.trace(), e.hops(), e.top_events()))
     (pa, ma, (oa, fa), ha, _), (pb, mb, (ob, fb), hb, nfast) = res
     assert all(np.array_equal(pa[k], pb[k]) for k in pa) and np.array_equal(ma, mb)
     assert np.array_equal(oa, ob) and np.array_equal(fa, fb) and ha == hb
