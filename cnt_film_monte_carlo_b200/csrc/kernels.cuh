@@ -578,7 +578,6 @@ __global__ void __launch_bounds__(256) gather_excitons_kernel(const ExcitonArray
   to.site[i] = from.site[s];
   to.heading[i] = from.heading[s];
   to.ndraw[i] = from.ndraw[s];
-  to.last_events[i] = from.last_events[s];
   to.gid[i] = from.gid[s];
 }
 

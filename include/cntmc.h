@@ -160,7 +160,15 @@ int cntmc_get_particles(const cntmc_t* h, int32_t* site, double* pos, double* de
 int cntmc_trace_enable(cntmc_t* h, int32_t cap);
 int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites);
 
-/* ---- tuning (never changes results) ------------------------------------------------------------------------------------ */
+/* ---- tuning (never changes results) ------------------------------------------------------------------------------------
+ * chunk_steps  time steps per hop-kernel launch (default 64)          stage_mb     cap on the staging buffer in MiB (0 = auto)
+ * hot_pct      share of the blocks that serve the most active excitons first (default 30)
+ * occupancy    resident 128-thread blocks per SM the hop kernel is compiled for (default 5)
+ * top_entries  1: the three widest entries of a row are tried before the row is searched (default)
+ * runs         1: chain walks over memory-consecutive sites read segment times instead of chasing records (default)
+ * dirs         1: last legs that leave from a site use stored unit vectors (default)
+ * stats        1: run the instrumented hop kernel (probe / crossing counters for cntmc_probes / cntmc_crossings)
+ * time_kernels 1: CUDA events around every hop-kernel launch (cntmc_last_kernel_ms) */
 int cntmc_set_option(cntmc_t* h, const char* name, int64_t value);
 int64_t cntmc_get_option(const cntmc_t* h, const char* name);
 /* device time of the last kubo_step / step call's kernels in milliseconds (CUDA events on the handle's stream) */
