@@ -402,6 +402,8 @@ void common_init(cntmc_t* h) {
   h->T.pos = h->d_pos.p;
   h->T.row = h->d_row.p;
   h->T.velocity = h->prm.velocity;
+  if (div_by_unsafe(h->prm.velocity)) throw std::invalid_argument("exciton velocity: a value whose binary significand is all ones is not supported");
+  h->T.inv_velocity = 1.0 / h->prm.velocity;
   h->time = 0;
   h->hops = h->reinjections = 0;
 }

@@ -146,6 +146,7 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
       e->T.rem_hi[c] = e->inj.rem_hi[c];
     }
     e->T.velocity = e->prm.velocity;
+    e->T.inv_velocity = 1.0 / e->prm.velocity;
     return 0;
   } catch (const std::exception& ex) {
     e->err = ex.what();
@@ -320,6 +321,16 @@ int64_t emul_select_top(const double* cum, int64_t d, double dice) {
   return -1;
 }
 int64_t emul_select_full(const double* cum, int64_t d, double dice) { return select_via_entries(cum, d, 0u, (uint32_t)d - 1u, dice); }
+// div_by against the division it replaces: number of operands (out of n) whose quotients differ
+int64_t emul_div_by_mismatches(const double* x, int64_t n, double c) {
+  const double rc = 1.0 / c;
+  int64_t      bad = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double a = x[i] / c, b = div_by(x[i], c, rc);
+    bad += memcmp(&a, &b, 8) != 0;
+  }
+  return bad;
+}
 void emul_philox2x32(uint32_t c0, uint32_t c1, uint32_t k, uint32_t* out) { philox2x32_10(c0, c1, k, out); }
 }  // extern "C"
 

@@ -160,6 +160,24 @@ def test_chain_walks_on_segment_times_are_bit_identical(golden):
         assert np.array_equal(oa, ob) and np.array_equal(fa, fb) and ha == hb and ha > 300
 
 
+def test_division_by_constants_is_the_ieee_division():
+    """div_by (reciprocal, exact remainder, correction) against x / c: the draws themselves, rate x draw products and
+    distances, for RAND_MAX and a set of velocities."""
+    import ctypes
+    e = Emul(base_mc())
+    f = e.L.emul_div_by_mismatches
+    f.restype = ctypes.c_int64
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double]
+    rng = np.random.default_rng(99)
+    draws = np.concatenate([np.arange(0, 1 << 16), (1 << 31) - 1 - np.arange(0, 1 << 16), rng.integers(0, 1 << 31, size=3_000_000)]).astype(np.float64)
+    assert f(draws.ctypes.data, len(draws), 2147483647.0) == 0
+    prod = np.ldexp(1.0 + rng.random(5_000_000), rng.integers(10, 90, size=5_000_000).astype(np.int32))
+    assert f(prod.ctypes.data, len(prod), 2147483647.0) == 0
+    dist = np.ldexp(1.0 + rng.random(2_000_000), -rng.integers(20, 50, size=2_000_000).astype(np.int32))
+    for v in (2e5, 1e5, 3.3e5, 123456.789, 1e4, 7.7e5):
+        assert f(dist.ctypes.data, len(dist), v) == 0
+
+
 def test_guided_search_equals_reference_loop_for_every_bucket():
     e = Emul(base_mc())
     rng = np.random.default_rng(5)
