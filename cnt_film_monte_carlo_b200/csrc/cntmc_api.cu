@@ -142,7 +142,6 @@ struct cntmc_handle {
 
   // device tables
   DevBuf<SiteRec> d_site;
-  DevBuf<TopRec> d_top;
   DevBuf<double> d_seg;
   DevBuf<DirRec> d_dir;
   DevBuf<PosRec>  d_pos;
@@ -331,7 +330,6 @@ void common_init(cntmc_t* h) {
   d_cell_start.upload(h->buckets.start, st);
   d_deg.alloc((size_t)N);
   h->d_site.upload(rec, st);
-  h->d_top.alloc((size_t)N);
   h->d_seg.upload(make_segment_times(rec), st);
   h->d_dir.upload(make_direction_records(rec, posrec), st);
   h->d_pos.upload(posrec, st);
@@ -352,7 +350,6 @@ void common_init(cntmc_t* h) {
   a.R.n_a1 = (int32_t)t.a1.size(); a.R.n_a2 = (int32_t)t.a2.size();
   a.deg = d_deg.p;
   a.site = h->d_site.p;
-  a.top = h->d_top.p;
   a.flags = h->d_flags.p;
   a.counters = h->d_counters.p;
 
@@ -396,7 +393,6 @@ void common_init(cntmc_t* h) {
   }
 
   h->T.site = h->d_site.p;
-  h->T.top = h->d_top.p;
   h->T.seg = h->opt_runs ? h->d_seg.p + kSegPad : nullptr;
   h->T.dir = h->opt_dirs ? h->d_dir.p : nullptr;
   h->T.pos = h->d_pos.p;

@@ -482,6 +482,7 @@ std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vec
     r.row_begin = r.row_len = 0;
     for (int k = 0; k < 8; ++k) r.guide[k] = 0;
     r.spare = 0.0;
+    r.top = TopRec{0, 0, 0, 0, 0, 0, {-1, -1, -1}, 0};  // filled by the table build
   }
   return rec;
 }

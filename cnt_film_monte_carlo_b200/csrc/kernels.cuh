@@ -647,7 +647,6 @@ struct CsrArgs {
   const uint64_t* row_begin;  // [N+1]    (fill pass; exclusive scan of deg)
   RowEntry*       row;        // [nnz]
   SiteRec*        site;       // rate fields of every record: total, 1/total, CSR row
-  TopRec*         top;        // [N] the three widest entries of every row
   int32_t*        flags;
   unsigned long long* counters;
 };
@@ -727,7 +726,7 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
     build_guide(CumView{a.row + base}, d, acc, g8);  // reads back this thread's own row
 #pragma unroll
     for (int j = 0; j < kGuideBuckets; ++j) a.site[i].guide[j] = g8[j];
-    top.store(a.top[i]);
+    top.store(a.site[i].top);
     if (d == 0) atomicOr(a.flags + FLAG_EMPTY_ROW, 1);
     if (guard) atomicAdd(a.counters + CTR_GUARD, 1ULL);
   }

@@ -22,7 +22,6 @@ struct Emul {
   Buckets              buckets;
   Injection            inj;
   std::vector<SiteRec> site;
-  std::vector<TopRec>  top;
   std::vector<double>  seg;
   std::vector<DirRec>  dir;
   bool                 runs = true;
@@ -78,7 +77,6 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
     const int64_t n = e->sites.N;
     std::vector<SiteGeom> geom((size_t)n);
     e->site = make_site_records(e->sites, e->prm.velocity, e->pos);
-    e->top.assign(e->site.size(), TopRec{});
     for (int64_t i = 0; i < n; ++i) {
       geom[i] = SiteGeom{e->sites.pos[0][i], e->sites.pos[1][i], e->sites.pos[2][i],
                          e->sites.orient[0][i], e->sites.orient[1][i], e->sites.orient[2][i]};
@@ -126,10 +124,9 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
       }
       e->site[i].row_begin = (uint32_t)e->row_ptr[i];
       e->site[i].row_len = d;
-      top.store(e->top[i]);
+      top.store(e->site[i].top);
       e->guards += guard;
     }
-    e->T.top = e->top.data();
     e->seg = make_segment_times(e->site);
     e->T.seg = e->runs ? e->seg.data() + kSegPad : nullptr;
     e->dir = make_direction_records(e->site, e->pos);
