@@ -118,7 +118,7 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-NCU_DRAM_BYTES_PER_EXCITON_STEP = (377.029376e6 + 1.285286e9) / (36 * 1_000_000)
+NCU_DRAM_BYTES_PER_EXCITON_STEP = (373.112320e6 + 1.285876e9) / (36 * 1_000_000)
 
 
 def algorithmic_bytes(hops, probes, crossings, P, launches):
@@ -294,12 +294,12 @@ def run_ours(args, rank, world, local_rank):
         peak, which = measured_hbm_peak()
         achieved = abytes / (k_ms * 1e-3) / 1e9
         # DRAM bytes per launch from the ncu --set full capture of this kernel on this workload
-        # (profiles/round1_r43_kubo_ncu_summary.txt: 0.377 GB read + 1.285 GB written by a 36-step launch over 1e6
-        # excitons = 46.2 B per exciton-step: the 32-byte (step, exciton) records plus the exciton state; the tables
+        # (profiles/round1_r44_kubo_ncu_summary.txt: 0.373 GB read + 1.286 GB written by a 36-step launch over 1e6
+        # excitons = 46.1 B per exciton-step: the 32-byte (step, exciton) records plus the exciton state; the tables
         # stay in L2), scaled to this run's launch size
         traffic = NCU_DRAM_BYTES_PER_EXCITON_STEP * P * n_int / max(1, k_n)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "ncu dram__bytes_{read,write}.sum, profiles/round1_r43_kubo_ncu_summary.txt, per exciton-step x launch size",
+                "traffic": traffic, "traffic_source": "ncu dram__bytes_{read,write}.sum, profiles/round1_r44_kubo_ncu_summary.txt, per exciton-step x launch size",
                 "peak_source": which, "kernel": "kubo_kernel",
                 "kernel_ms_per_launch": k_ms / max(1, k_n), "kernel_share_of_step": k_ms / step_ms,
                 "bytes_per_hop": abytes / max(1, hops), "probes_per_hop": probes / max(1, hops),
