@@ -73,6 +73,10 @@ def test_error_reporting():
         e.set_option("nope", 1)
     e.set_option("chunk_steps", 16)
     assert e.get_option("chunk_steps") == 16
+    for name in ("top_entries", "runs", "dirs"):  # the shortcuts of the hop kernel are on by default and can be switched off
+        assert e.get_option(name) == 1
+        e.set_option(name, 0)
+        assert e.get_option(name) == 0
 
 
 def test_mesh_loader_errors(tmp_path):
