@@ -178,6 +178,39 @@ def test_division_by_constants_is_the_ieee_division():
         assert f(dist.ctypes.data, len(dist), v) == 0
 
 
+def test_shortcuts_on_random_trim_boxes():
+    """Random small films cut by random trim boxes (the swap-with-last trim permutes sites, so runs of memory-consecutive
+    chain neighbours break in arbitrary places): segment-time walks + stored directions + top entries change nothing."""
+    rng = np.random.default_rng(2024)
+    tried = 0
+    for case in range(12):
+        pos, ori = film.film(NT=int(rng.integers(20, 60)), NP=int(rng.integers(8, 40)), a=float(rng.choice([2.0, 5.0])),
+                             LX=float(rng.uniform(60, 160)), LY=float(rng.uniform(20, 60)), seed=int(rng.integers(1, 1 << 30)))
+        lo, hi = pos.reshape(3, -1).min(axis=1) * 1e-9, pos.reshape(3, -1).max(axis=1) * 1e-9
+        cut = rng.uniform(0.0, 0.3, size=(3, 2)) * (hi - lo)[:, None]
+        mc = dict(base_mc())
+        mc["trim limits"] = {k: [float(lo[i] + cut[i, 0]), float(hi[i] - cut[i, 1])] for i, k in enumerate(("xlim", "ylim", "zlim"))}
+        states = []
+        try:
+            for on in (False, True):
+                e = Emul(mc)
+                e.kubo_init(pos, ori)
+                if len(e.inject()) == 0 or not np.all(np.diff(e.csr()[0]) > 0):
+                    raise ValueError("empty injection region or a site without neighbours")  # the engine refuses these
+                e.set_runs(on)
+                e.set_top_entries(on)
+                e.create_philox(150, seed=case + 1)
+                msd = e.kubo_step(1e-13 if case % 2 else 4e-13, 60, trace_cap=1 << 12)
+                states.append((e.particles(), msd, e.trace(), e.hops()))
+        except (ValueError, AssertionError):
+            continue  # e.g. an empty injection region or an isolated site after the cut: not what this test is about
+        tried += 1
+        (pa, ma, (oa, fa), ha), (pb, mb, (ob, fb), hb) = states
+        assert all(np.array_equal(pa[k], pb[k]) for k in pa) and np.array_equal(ma, mb), case
+        assert np.array_equal(oa, ob) and np.array_equal(fa, fb) and ha == hb, case
+    assert tried >= 6
+
+
 def test_guided_search_equals_reference_loop_for_every_bucket():
     e = Emul(base_mc())
     rng = np.random.default_rng(5)
