@@ -398,7 +398,6 @@ void common_init(cntmc_t* h) {
   h->T.pos = h->d_pos.p;
   h->T.row = h->d_row.p;
   h->T.velocity = h->prm.velocity;
-  if (div_by_unsafe(h->prm.velocity)) throw std::invalid_argument("exciton velocity: a value whose binary significand is all ones is not supported");
   h->T.inv_velocity = 1.0 / h->prm.velocity;
   h->time = 0;
   h->hops = h->reinjections = 0;
@@ -643,6 +642,9 @@ int cntmc_create(const char* json_text, cntmc_t** out) {
     const json::Value      doc = json::parse(json_text);
     h->block = mc_block(doc);
     h->prm = parse_params(h->block);
+    // the kernels divide by the velocity with div_by (hop_core.h), which is exact for every divisor but these
+    if (div_by_unsafe(h->prm.velocity))
+      throw std::invalid_argument("\"exciton velocity [m/s]\": a value whose binary significand is all ones is not supported");
     *out = h.release();
   });
 }

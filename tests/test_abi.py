@@ -60,6 +60,8 @@ def test_error_reporting():
     del mc["max hopping radius [m]"]
     with pytest.raises(CntmcError, match="max hopping radius"):
         Engine(mc)
+    with pytest.raises(CntmcError, match="significand is all ones"):   # the one kind of divisor div_by is not exact for
+        Engine(base_mc(**{"exciton velocity [m/s]": float(np.nextafter(262144.0, 0.0))}))
     e = Engine(base_mc(**{"rate type": "dexter"}))
     e.set_mesh(np.zeros((3, 2, 2)), np.ones((3, 2, 2)))
     with pytest.raises(CntmcError, match="rate type must be one of"):  # monte_carlo.cpp:59
