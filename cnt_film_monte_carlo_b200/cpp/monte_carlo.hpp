@@ -174,12 +174,13 @@ class monte_carlo {
         << double(pop[i]) / (_area[i] * dy) << "\n";
     f.close();
   }
-  // monte_carlo.h:786-818; the exciton's stream is (seed, fileNo); max_steps bounds the reference's unbounded loop
+  // monte_carlo.h:786-818; the exciton's stream is (seed, 2^63 | fileNo) -- a domain of its own, so that a tracked exciton
+  // never shares draws with exciton fileNo of the population; max_steps bounds the reference's unbounded loop
   bool track_particle(double dt, int fileNo, int64_t max_steps = int64_t(1) << 20) {
     std::vector<double> path((size_t)max_steps * 3);
     int64_t             n = 0;
     int32_t             reached = 0;
-    ok(cntmc_track_particle(_h, dt, _seed, (uint64_t)fileNo, 0, nullptr, nullptr, max_steps, path.data(), &n, &reached));
+    ok(cntmc_track_particle(_h, dt, _seed, (1ull << 63) | (uint64_t)fileNo, 0, nullptr, nullptr, max_steps, path.data(), &n, &reached));
     std::ofstream file((_output_directory / ("particle_path." + std::to_string(fileNo) + ".dat")).string(), std::ios::out);
     file << std::scientific << std::showpos;
     for (int64_t s = 0; s < n; ++s) file << "   " << path[3 * s] << " " << path[3 * s + 1] << " " << path[3 * s + 2] << "\n";

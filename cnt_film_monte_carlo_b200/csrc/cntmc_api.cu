@@ -84,20 +84,20 @@ struct ExcitonStore {
   DevBuf<double>   px, py, pz, dx, dy, dz, ff;
   DevBuf<int32_t>  site;
   DevBuf<uint8_t>  heading;
-  DevBuf<uint32_t> ndraw, events;
+  DevBuf<uint32_t> ndraw;
   DevBuf<uint64_t> gid;
   void alloc(size_t n, bool with_gid) {
     px.alloc(n); py.alloc(n); pz.alloc(n);
     dx.alloc(n); dy.alloc(n); dz.alloc(n);
     ff.alloc(n);
-    site.alloc(n); heading.alloc(n); ndraw.alloc(n); events.alloc(n);
+    site.alloc(n); heading.alloc(n); ndraw.alloc(n);
     if (with_gid) gid.alloc(n);
   }
   void swap(ExcitonStore& o) {
     px.swap(o.px); py.swap(o.py); pz.swap(o.pz);
     dx.swap(o.dx); dy.swap(o.dy); dz.swap(o.dz);
     ff.swap(o.ff);
-    site.swap(o.site); heading.swap(o.heading); ndraw.swap(o.ndraw); events.swap(o.events); gid.swap(o.gid);
+    site.swap(o.site); heading.swap(o.heading); ndraw.swap(o.ndraw); gid.swap(o.gid);
   }
   ExcitonArrays view(bool with_gid) const {
     ExcitonArrays S{};
@@ -107,7 +107,6 @@ struct ExcitonStore {
     S.site = site.p;
     S.heading = heading.p;
     S.ndraw = ndraw.p;
-    S.last_events = events.p;
     S.gid = with_gid ? gid.p : nullptr;
     return S;
   }
@@ -157,7 +156,6 @@ struct cntmc_handle {
   DevBuf<uint8_t>  d_alive;
   uint64_t         next_gid = 0;
   DevBuf<char>     sort_tmp;
-  bool             have_events = false;
   DrawConfig       draws{};
   bool             replay = false;
   DevBuf<int64_t>  r_off;
@@ -167,10 +165,14 @@ struct cntmc_handle {
   // reductions, diagnostics
   DevBuf<double>             d_partial, d_sums;
   DevBuf<StageRec>           d_stage;
-  DevBuf<uint32_t>           d_list[2][kClasses], d_list_count[2];
+  DevBuf<uint32_t>           d_list[2][kClasses], d_list_count[2], d_defer_list, d_defer_count;
   DevBuf<unsigned long long> d_list_head;
+  DevBuf<double>             d_cur_dt, d_cur_ox, d_cur_oy, d_cur_oz;  // cursors of the excitons deferred to the group solver
+  DevBuf<int32_t>            d_cur_step;
+  DevBuf<uint32_t>           d_cur_nevent;
   int                        cur_list = 0;
   bool                       have_lists = false;
+  double                     lists_deep_thr = 0;  // the class boundary the lists were filed with
   DevBuf<int32_t>            d_flags;
   DevBuf<unsigned long long> d_counters;
   DevBuf<int32_t>            d_trace_sites, d_trace_counts;
@@ -182,12 +184,13 @@ struct cntmc_handle {
 
   // tuning
   int64_t opt_chunk = 64;     // time steps per launch
-  int64_t opt_sort = 1;       // (kept for compatibility; activity classes replaced the sort)
   int64_t opt_dirs = 1;         // last legs that leave from a site use stored unit vectors
   int64_t opt_runs = 1;         // chain walks over memory-consecutive sites read segment times instead of chasing records
   int64_t opt_top_entries = 1;  // the three widest entries of a row are tried before the row is searched
-  int64_t opt_hot_pct = 30;   // share of the blocks that serve the most active classes first
-  int64_t opt_block = 128;  // threads per block of the hop kernel
+  int64_t opt_hot_pct = 30;   // share of the lane blocks that serve the most active classes first
+  int64_t opt_deep_thr = 16;  // Gamma*dt from which an exciton belongs to the group solver (0: no group solver)
+  int64_t opt_deep_pct = 20;  // share of the blocks that run the group solver in the first pass of a launch
+  int64_t opt_park_min_s = 1, opt_park_min_e = 1, opt_park_age = 4;  // parking of the minority operation in lane blocks
   int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
   int64_t opt_stage_mb = 0;  // cap on the (step, exciton) staging buffer in MiB; shortens the launches if needed.
                              // 0 = a third of the device memory that is free when the buffer is first sized
@@ -235,7 +238,7 @@ void cntmc_handle::reserve_contact(int64_t cap, int64_t keep) {
   grow_keep(ex.dx, c, k, stream); grow_keep(ex.dy, c, k, stream); grow_keep(ex.dz, c, k, stream);
   grow_keep(ex.ff, c, k, stream);
   grow_keep(ex.site, c, k, stream); grow_keep(ex.heading, c, k, stream); grow_keep(ex.ndraw, c, k, stream);
-  grow_keep(ex.events, c, k, stream); grow_keep(ex.gid, c, k, stream);
+  grow_keep(ex.gid, c, k, stream);
   ex_spare.alloc(c, true);
   d_alive.alloc(c);
   e_iota.alloc(c);
@@ -266,6 +269,10 @@ void check_flags(cntmc_t* h) {
   int32_t flags[FLAG_COUNT];
   h->d_flags.download(flags, FLAG_COUNT, h->stream);
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (flags[FLAG_REPLAY] || flags[FLAG_STUCK]) {  // reported once: a fresh population can use the handle again
+    CUDA_CHECK(cudaMemsetAsync(h->d_flags.p, 0, 2 * sizeof(int32_t), h->stream));
+    static_assert(FLAG_STUCK == 0 && FLAG_REPLAY == 1, "the two run-time flags are the first two words");
+  }
   if (flags[FLAG_REPLAY]) throw ReplayError("a replayed draw list ran out before the end of the run");
   if (flags[FLAG_STUCK]) throw StateError("an exciton exceeded the chain-walk guard (coincident chain sites?)");
 }
@@ -424,14 +431,13 @@ void create_common(cntmc_t* h, int64_t P) {
   require(!h->inj.sites.empty(), "the injection region holds no site");
   use_device(h);
   h->alloc_excitons(P);
+  if (P != h->P) h->trace_cap = 0;  // the trace buffers were sized for the previous population
   h->P = P;
-  h->have_events = false;
   h->have_lists = false;
   h->time = 0;
   h->hops = h->reinjections = 0;
   h->crossings = h->probes = 0;
   CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, CTR_COUNT * sizeof(unsigned long long), h->stream));
-  CUDA_CHECK(cudaMemsetAsync(h->ex.events.p, 0, (size_t)P * sizeof(uint32_t), h->stream));
   if (h->replay)
     launch_create<ReplayDraws>(h, P, h->d_inject.p, (int32_t)h->inj.sites.size());
   else
@@ -446,8 +452,6 @@ void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st
   switch (h->opt_occupancy) {
     case 4: kubo_kernel<Draws, 4, kInstr><<<grid, 128, 0, st>>>(a); break;
     case 6: kubo_kernel<Draws, 6, kInstr><<<grid, 128, 0, st>>>(a); break;
-    case 7: kubo_kernel<Draws, 7, kInstr><<<grid, 128, 0, st>>>(a); break;
-    case 8: kubo_kernel<Draws, 8, kInstr><<<grid, 128, 0, st>>>(a); break;
     default: kubo_kernel<Draws, 5, kInstr><<<grid, 128, 0, st>>>(a); break;
   }
 }
@@ -510,13 +514,27 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     for (int c = 0; c < kClasses; ++c) h->d_list[b][c].alloc((size_t)h->P);
     h->d_list_count[b].alloc(kClasses);
   }
-  h->d_list_head.alloc(kClasses);
+  h->d_list_head.alloc(kLists);
+  // group solver (counter-based streams only: a replayed stream has nothing to prepare in parallel)
+  const bool   deep = h->opt_deep_thr > 0 && h->opt_deep_pct > 0 && !h->replay;
+  const double deep_thr = deep ? (double)h->opt_deep_thr : INFINITY;
+  h->d_defer_list.alloc((size_t)h->P);
+  h->d_defer_count.alloc(1);
+  if (deep) {
+    h->d_cur_dt.alloc((size_t)h->P); h->d_cur_ox.alloc((size_t)h->P); h->d_cur_oy.alloc((size_t)h->P); h->d_cur_oz.alloc((size_t)h->P);
+    h->d_cur_step.alloc((size_t)h->P);
+    h->d_cur_nevent.alloc((size_t)h->P);
+  }
   auto lists = [&](int read_buf) {
     ClassLists q{};
     for (int c = 0; c < kClasses; ++c) {
       q.list[c] = h->d_list[read_buf][c].p;
       q.next_list[c] = h->d_list[1 - read_buf][c].p;
     }
+    q.list[kDeferred] = h->d_defer_list.p;
+    q.deferred_count_in = h->d_defer_count.p;
+    q.defer_list = h->d_defer_list.p;
+    q.defer_count = h->d_defer_count.p;
     q.count = h->d_list_count[read_buf].p;
     q.next_count = h->d_list_count[1 - read_buf].p;
     q.head = h->d_list_head.p;
@@ -524,24 +542,38 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   };
   h->last_launches = 0;
   CUDA_CHECK(cudaEventRecord(h->ev0, st));
-  if (!h->have_lists) {  // population just created or uploaded: file everything once
+  if (!h->have_lists || h->lists_deep_thr != deep_thr) {  // population just created or uploaded: file everything once
     CUDA_CHECK(cudaMemsetAsync(h->d_list_count[h->cur_list].p, 0, kClasses * sizeof(uint32_t), st));
-    classify_kernel<<<(unsigned)((h->P + 255) / 256), 256, 0, st>>>(h->T, h->ex.site.p, h->P, dt, lists(1 - h->cur_list));
+    classify_kernel<<<(unsigned)((h->P + 255) / 256), 256, 0, st>>>(h->T, h->ex.site.p, h->P, dt, deep_thr, lists(1 - h->cur_list));
     CUDA_CHECK(cudaGetLastError());
     h->have_lists = true;
+    h->lists_deep_thr = deep_thr;
     h->last_launches += 1;
   }
   for (int64_t done = 0; done < nsteps; done += chunk) {
     const int n = (int)std::min(chunk, nsteps - done);
-    CUDA_CHECK(cudaMemsetAsync(h->d_list_head.p, 0, kClasses * sizeof(unsigned long long), st));
+    CUDA_CHECK(cudaMemsetAsync(h->d_list_head.p, 0, kLists * sizeof(unsigned long long), st));
     CUDA_CHECK(cudaMemsetAsync(h->d_list_count[1 - h->cur_list].p, 0, kClasses * sizeof(uint32_t), st));
+    CUDA_CHECK(cudaMemsetAsync(h->d_defer_count.p, 0, sizeof(uint32_t), st));
     KuboArgs a{};
     a.T = h->T;
     a.S = h->arrays();
+    a.C.dt_rem = h->d_cur_dt.p; a.C.ox = h->d_cur_ox.p; a.C.oy = h->d_cur_oy.p; a.C.oz = h->d_cur_oz.p;
+    a.C.step = h->d_cur_step.p;
+    a.C.nevent = h->d_cur_nevent.p;
     a.draws = h->draws;
     a.q = lists(h->cur_list);
-    a.hot_blocks = (int32_t)((int64_t)grid * h->opt_hot_pct / 100);
+    a.pass = 1;
+    a.deep_blocks = deep ? std::max<int32_t>(1, (int32_t)((int64_t)grid * h->opt_deep_pct / 100)) : 0;
+    if (a.deep_blocks >= (int32_t)grid) a.deep_blocks = (int32_t)grid - 1;
+    if (a.deep_blocks < 0) a.deep_blocks = 0;
+    a.hot_blocks = (int32_t)(((int64_t)grid - a.deep_blocks) * h->opt_hot_pct / 100);
     a.top_entries = (int32_t)h->opt_top_entries;
+    a.deep_thr = a.deep_blocks > 0 ? deep_thr : INFINITY;
+    a.deep_rate = a.deep_thr / dt;
+    a.park_min_s = (int32_t)h->opt_park_min_s;
+    a.park_min_e = (int32_t)h->opt_park_min_e;
+    a.park_age = (int32_t)h->opt_park_age;
     a.P = h->P;
     a.dt = dt;
     a.nsteps = n;
@@ -559,18 +591,22 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
       h->kernel_events.push_back(k1);
       CUDA_CHECK(cudaEventRecord(k0, st));
     }
-    if (h->replay)
-      launch_kubo<ReplayDraws>(h, a, grid, st);
-    else
-      launch_kubo<PhiloxDraws>(h, a, grid, st);
-    CUDA_CHECK(cudaGetLastError());
+    for (int pass = 1; pass <= (a.deep_blocks > 0 ? 2 : 1); ++pass) {
+      a.pass = pass;  // 2: the excitons the lane blocks deferred, all blocks run the group solver
+      if (h->replay)
+        launch_kubo<ReplayDraws>(h, a, grid, st);
+      else
+        launch_kubo<PhiloxDraws>(h, a, grid, st);
+      CUDA_CHECK(cudaGetLastError());
+      h->last_launches += 1;
+    }
     if (k1) CUDA_CHECK(cudaEventRecord(k1, st));
     h->cur_list = 1 - h->cur_list;
     reduce_stage_kernel<<<dim3((unsigned)n, kStageSplits), 256, 0, st>>>(h->d_stage.p, h->P, n, h->d_partial.p);
     CUDA_CHECK(cudaGetLastError());
     finish_sums_kernel<<<(n * 4 + 127) / 128, 128, 0, st>>>(h->d_partial.p, n, dev_sums + done * 4);
     CUDA_CHECK(cudaGetLastError());
-    h->last_launches += 3;
+    h->last_launches += 2;
   }
   CUDA_CHECK(cudaEventRecord(h->ev1, st));
   for (int64_t s = 0; s < nsteps; ++s) h->time += dt;  // monte_carlo.cpp:341, one addition per step
@@ -807,7 +843,14 @@ int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P,
     require(P > 0 && site && pos && delta && ff && heading && ndraw, "bad host-state arguments");
     use_device(h);
     cudaStream_t st = h->stream;
+    // the kernels index the site tables with what the caller hands in: refuse what would read out of bounds
+    const int64_t N = h->sites.N;
+    for (int64_t i = 0; i < P; ++i) {
+      if (site[i] < 0 || (int64_t)site[i] >= N) throw std::invalid_argument("host state: site index out of range");
+      if (!std::isfinite(ff[i])) throw std::invalid_argument("host state: free-flight time is not finite");
+    }
     if (P > h->capacity) h->alloc_excitons(P);
+    if (P != h->P) h->trace_cap = 0;  // the trace buffers were sized for the previous population
     h->have_lists = false;  // the uploaded population has not been filed under activity classes yet
     h->P = P;
     const size_t n = (size_t)P;
@@ -1245,16 +1288,23 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     if (k == "chunk_steps") {
       require(value >= 1 && value <= 256, "chunk_steps must be in [1, 256]");
       h->opt_chunk = value;
-    } else if (k == "sort") {
-      h->opt_sort = value ? 1 : 0;
-    } else if (k == "block") {
-      require(value == 32 || value == 64 || value == 128, "block must be 32, 64 or 128");
-      h->opt_block = value;
+    } else if (k == "deep_thr") {
+      require(value >= 0 && value <= 1000000, "deep_thr must be in [0, 1e6] (0 = no group solver)");
+      h->opt_deep_thr = value;
+    } else if (k == "deep_pct") {
+      require(value >= 0 && value <= 90, "deep_pct must be in [0, 90]");
+      h->opt_deep_pct = value;
+    } else if (k == "park_min_s" || k == "park_min_e") {
+      require(value >= 1 && value <= 32, "park_min_* must be in [1, 32]");
+      (k == "park_min_s" ? h->opt_park_min_s : h->opt_park_min_e) = value;
+    } else if (k == "park_age") {
+      require(value >= 1 && value <= 1024, "park_age must be in [1, 1024]");
+      h->opt_park_age = value;
     } else if (k == "hot_pct") {
       require(value >= 0 && value <= 100, "hot_pct must be in [0, 100]");
       h->opt_hot_pct = value;
     } else if (k == "occupancy") {
-      require(value >= 4 && value <= 8, "occupancy must be 4 to 8 blocks per SM");
+      require(value >= 4 && value <= 6, "occupancy must be 4 to 6 blocks per SM");
       h->opt_occupancy = value;
     } else if (k == "dirs") {
       h->opt_dirs = value ? 1 : 0;
@@ -1279,10 +1329,13 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
 int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   const std::string k = name ? name : "";
   if (k == "chunk_steps") return h->opt_chunk;
-  if (k == "sort") return h->opt_sort;
-  if (k == "block") return h->opt_block;
   if (k == "occupancy") return h->opt_occupancy;
   if (k == "hot_pct") return h->opt_hot_pct;
+  if (k == "deep_thr") return h->opt_deep_thr;
+  if (k == "deep_pct") return h->opt_deep_pct;
+  if (k == "park_min_s") return h->opt_park_min_s;
+  if (k == "park_min_e") return h->opt_park_min_e;
+  if (k == "park_age") return h->opt_park_age;
   if (k == "top_entries") return h->opt_top_entries;
   if (k == "runs") return h->opt_runs;
   if (k == "dirs") return h->opt_dirs;

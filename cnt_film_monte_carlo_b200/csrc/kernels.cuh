@@ -26,7 +26,6 @@ struct ExcitonArrays {
   int32_t*  site;          // particle::_scat_ptr
   uint8_t*  heading;       // particle::_heading_right
   uint32_t* ndraw;         // next draw index of the exciton's stream
-  uint32_t* last_events;   // (unused since the activity classes; kept in the layout of uploads / compaction)
   uint64_t* gid;           // stream id where excitons are created and destroyed (contact mode); null = first_gid + index
 };
 
@@ -114,26 +113,33 @@ __global__ void __launch_bounds__(256) create_excitons_kernel(const CreateArgs a
   init_draws(D, a.draws, a.S, e);
   create_exciton(L, a.T, D, a.site_list, a.n_list);
   store_lane(L, a.S, e);
-  a.S.last_events[e] = 0;
   if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
 }
 
 // ---- K2: the hop kernel, Green-Kubo flavour -------------------------------------------------------------------------------
-// Activity classes.  Exciton activity is extremely skewed (on the C2 film the median exciton scatters twice in 64 steps,
-// the 99th percentile 1400 times: a few excitons sit in traps between closely crossing tubes) and it is predictable from
-// the state: Gamma(site) * dt = expected events per step if the exciton stays where it is.  When a lane stores an
-// exciton it files it under one of four classes; in the next launch "hot" blocks serve the two active classes and
-// "cold" blocks the two quiet ones, so that warps mostly hold excitons that run the same branch of the loop.
-constexpr int kClasses = 4;
-__device__ __forceinline__ int activity_class(double expected_events_per_step) {
-  return expected_events_per_step >= 8.0 ? 3 : expected_events_per_step >= 1.0 ? 2 : expected_events_per_step >= 0.125 ? 1 : 0;
+// Activity classes.  Exciton activity is extremely skewed and predictable from the state: Gamma(site) * dt = expected
+// events per step if the exciton stays where it is.  On the C2 film 83 % of the sites have Gamma*dt < 0.125; 17 % sit
+// in "traps" -- two to five neighbouring sites of one tube whose mutual rate is the table's maximum (8.78e13/s, so
+// Gamma*dt = 8.8 per partner): an exciton there scatters 9 to 38 times per step until a flight carries it out.  1 % of
+// the excitons make a third of all events (deep traps, two or more partners), another 7 % a second third.
+// When a lane stores an exciton it files it under one of five classes; in the next launch "hot" blocks serve the
+// active classes and "cold" blocks the quiet ones, so that warps mostly hold excitons that run the same branch of the
+// loop, and class 4 (the deep traps) goes to the blocks that run the group solver (see hop_loop).
+constexpr int kClasses = 5;
+constexpr int kLists = kClasses + 1;  // + the excitons deferred to the group solver during the launch
+constexpr int kDeferred = kClasses;
+__device__ __forceinline__ int activity_class(double ev, double deep_thr) {
+  return ev >= deep_thr ? 4 : ev >= 8.0 ? 3 : ev >= 1.0 ? 2 : ev >= 0.125 ? 1 : 0;
 }
 struct ClassLists {
-  const uint32_t*     list[kClasses];       // excitons of each class, filed by the previous launch
-  const uint32_t*     count;                // [kClasses]
-  unsigned long long* head;                 // [kClasses] next unassigned position of each list
-  uint32_t*           next_list[kClasses];  // being filled for the next launch
-  uint32_t*           next_count;           // [kClasses]
+  const uint32_t*     list[kLists];           // excitons of each class, filed by the previous launch; [kDeferred]: this launch
+  const uint32_t*     count;                  // [kClasses]
+  const uint32_t*     deferred_count_in;      // count of list[kDeferred] (second pass)
+  unsigned long long* head;                   // [kLists] next unassigned position of each list
+  uint32_t*           next_list[kClasses];    // being filled for the next launch
+  uint32_t*           next_count;             // [kClasses]
+  uint32_t*           defer_list;             // being filled by the lane blocks of this launch
+  uint32_t*           defer_count;
 };
 
 // file exciton e of the lanes flagged `mine` under their class `cls` (warp-aggregated append; call with the whole warp)
@@ -150,15 +156,27 @@ __device__ __forceinline__ void file_excitons(const ClassLists& q, bool mine, in
     }
   }
 }
-// hand an exciton to every lane that `want`s one, from the two classes of the warp's current role: hot warps serve
-// classes 3 then 2, cold warps classes 0 then 1 (call with the whole warp).  Returns false for lanes left without work.
-__device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, bool hot_role, int lane, unsigned lt_mask, int64_t& e) {
+__device__ __forceinline__ void defer_excitons(const ClassLists& q, bool mine, uint32_t e, int lane, unsigned lt_mask) {
+  const unsigned m = __ballot_sync(0xffffffffu, mine);
+  if (m) {
+    uint32_t  base = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(q.defer_count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (mine) q.defer_list[base + __popc(m & lt_mask)] = e;
+  }
+}
+// hand an exciton to every lane that `want`s one, from the n_serve lists named in `serve`, in that order (call with the
+// whole warp).  Returns false for lanes left without work.
+// serve: list numbers, four bits each, first one in the low bits
+__device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, uint32_t serve, int n_serve, int lane, unsigned lt_mask,
+                                             int64_t& e) {
   bool     got = false;
   unsigned need = __ballot_sync(0xffffffffu, want);
-  for (int k = 0; k < 2 && need; ++k) {
-    const int          c = hot_role ? kClasses - 1 - k : k;
+  for (int k = 0; k < n_serve && need; ++k) {
+    const int          c = (int)((serve >> (4 * k)) & 15u);
     const int          n = __popc(need), leader = __ffs(need) - 1;
-    const long long    cnt = (long long)q.count[c];
+    const long long    cnt = (long long)(c == kDeferred ? *q.deferred_count_in : q.count[c]);
     unsigned long long base = 0;
     if (lane == leader) base = (cnt > 0) ? atomicAdd(q.head + c, (unsigned long long)n) : (unsigned long long)cnt;
     base = __shfl_sync(0xffffffffu, base, leader);
@@ -175,7 +193,6 @@ __device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, boo
   return got;
 }
 
-
 #if defined(CNTMC_PROFILE_SEGMENTS)
 constexpr int kWarpTimeCols = 12;  // + cycles per loop segment of lane 0
 #else
@@ -184,14 +201,26 @@ constexpr int kWarpTimeCols = 4;
 struct alignas(32) StageRec {  // one full 32-byte sector per (step, exciton)
   double dx2, dy2, dz2, events;
 };
+// where an exciton stood when a lane block handed it to the group solver in the middle of a launch
+struct CursorArrays {
+  double *  dt_rem, *ox, *oy, *oz;  // time left in the current step, particle::_old_pos of the step
+  int32_t*  step;
+  uint32_t* nevent;                 // events of the current step so far
+};
 
 struct KuboArgs {
   Tables              T;
   ExcitonArrays       S;
+  CursorArrays        C;
   DrawConfig          draws;
   ClassLists          q;
-  int32_t             hot_blocks;  // blocks [0, hot_blocks) serve the active classes first
-  int32_t             top_entries; // try the three widest entries of a row before searching it
+  int32_t             pass;         // 1: every list of the launch; 2: the excitons deferred during pass 1 (all blocks run the group solver)
+  int32_t             deep_blocks;  // blocks [0, deep_blocks) run the group solver on class 4
+  int32_t             hot_blocks;   // of the lane blocks, the first hot_blocks serve the active classes first
+  int32_t             top_entries;  // try the three widest entries of a row before searching it
+  double              deep_thr;     // Gamma*dt from which an exciton belongs to the group solver (inf: never)
+  double              deep_rate;    // the same as a rate: deep_thr / dt
+  int32_t             park_min_s, park_min_e, park_age;  // lane blocks: see hop_loop
   int64_t             P;
   double              dt;
   int32_t             nsteps;
@@ -204,37 +233,116 @@ struct KuboArgs {
   unsigned long long* warp_times;  // diagnostics (instrumented kernel): [warps][4] = enter, first failed take, exit, role
 };
 
-// Persistent warps; every lane owns one exciton at a time, carries it through all nsteps time steps of the launch, files
-// it under its activity class for the next launch and takes another one (see ClassLists).
+// Draw source of the group solver: G lanes share one exciton, and lane j of the group prepares the two draws of the j-th
+// event from now -- Philox2x32-10 and the logarithm of the free-flight draw, the two longest dependency chains of an
+// event -- while its neighbours prepare the others.  The stream is counter-based, so this is the same sequence the
+// one-lane source produces, fetched with a shuffle instead of computed in line; anything that does not fit the pattern
+// (a re-injection draw, a zero draw) is served from the same batch or computed directly.
+template <int G>
+struct GroupDraws {
+  PhiloxDraws base;
+  uint32_t    nd0, r1, r2;
+  double      lg;
+  unsigned    gmask;
+  int         gbase, j;
+  bool        valid;
+  __device__ __forceinline__ void init(uint64_t seed, uint64_t gid) {
+    base.init(seed, gid);
+    const int lane = threadIdx.x & 31;
+    gbase = lane & ~(G - 1);
+    j = lane - gbase;
+    gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    valid = false;
+    nd0 = 0;
+  }
+  __device__ __forceinline__ void refill(uint32_t ndraw) {
+    nd0 = ndraw;
+    uint32_t    n = ndraw + 2u * (uint32_t)j;
+    PhiloxDraws t = base;
+    t.blk = 0xffffffffu;
+    r1 = (uint32_t)t.next(n);
+    r2 = (uint32_t)t.next(n);
+    lg = r2 ? fast_log_unit(div_by((double)r2, kRandMax, kInvRandMax)) : 0.0;
+    valid = true;
+  }
+  __device__ __forceinline__ int32_t next(uint32_t& ndraw) {
+    uint32_t off = ndraw - nd0;
+    if (!valid || off >= 2u * G) {
+      refill(ndraw);
+      off = 0;
+    }
+    const uint32_t v = __shfl_sync(gmask, (off & 1u) ? r2 : r1, gbase + (int)(off >> 1));
+    ++ndraw;
+    return (int32_t)v;
+  }
+  __device__ __forceinline__ double log_ratio(int32_t r, uint32_t ndraw_after) const {
+    const uint32_t off = ndraw_after - 1u - nd0;
+    if (valid && off < 2u * G && (off & 1u)) return __shfl_sync(gmask, lg, gbase + (int)(off >> 1));
+    return fast_log_unit(div_by((double)r, kRandMax, kInvRandMax));
+  }
+  __device__ __forceinline__ bool exhausted() const { return false; }
+};
+template <int G>
+__device__ __forceinline__ void init_draws(GroupDraws<G>& D, const DrawConfig& dc, const ExcitonArrays& S, int64_t e) {
+  D.init(dc.seed, S.gid ? S.gid[e] : dc.first_gid + (uint64_t)e);
+}
+template <typename Draws, int G>
+struct LoopDraws {
+  typedef GroupDraws<G> type;
+};
+template <typename Draws>
+struct LoopDraws<Draws, 1> {
+  typedef Draws type;
+};
+
+// The loop of the hop kernel.  Persistent warps; every group of G lanes owns one exciton at a time, carries it through
+// the time steps of the launch, files it under its activity class for the next launch and takes another one.
 //
-// The loop is flat: an iteration moves every busy lane forward by one scattering event or by the end of one time step,
-// whichever comes first for that lane; lanes of a warp are in general in different time steps of different excitons.
-// Nothing in the loop needs a barrier, shared memory or a floating-point atomic: when a lane ends a step it writes its
+// G = 1 (lane blocks): one exciton per lane.  The loop is flat: an iteration moves every busy lane forward by the end of
+// one time step and / or one scattering event; lanes of a warp are in general in different time steps of different
+// excitons.  Nothing in the loop needs a barrier or a floating-point atomic: when a lane ends a step it writes its
 // squared displacement to the (step, exciton) record, and reduce_stage_kernel sums the records in a fixed order
-// afterwards, so the ensemble sums do not depend on which lane happened to process which exciton, nor on any tuning
-// option.
+// afterwards, so the ensemble sums do not depend on which lane processed which exciton, nor on any tuning option.
+//   Parking: a warp pays the latency of the step-end path and of the event path whenever at least one lane needs
+//   each.  With park_min_s / park_min_e > 1 the path that fewer than that many lanes ask for is skipped (its lanes
+//   wait, at most park_age iterations) until enough lanes have gathered.
+//   Deferral: an exciton that lands in a deep trap (Gamma*dt >= deep_thr) would occupy its lane for thousands of
+//   sequential events while the other 31 idle at the end of the launch; the lane stores it with its cursor (step, time
+//   left, events of the step, start-of-step position) and a second pass of the group solver finishes its launch.
+//
+// G > 1 (group solver): the G lanes of a group hold the same exciton and execute the same instructions on the same
+// values; what they share is the work that does not depend on the event chain -- the draws and logarithms of the next
+// G events (GroupDraws).  A trapped exciton's events then cost a short chain each (flight compare, dice, top entries,
+// destination record, 1/Gamma times a prepared logarithm) instead of that plus Philox plus log, and at most 32/G
+// excitons diverge inside a warp instead of 32.  Results are the same bits: same draws, same arithmetic, same order.
+// Only the first lane of a group stores anything.
+//
 // kInstr adds what only tests and the roofline bookkeeping need (site traces, probe / crossing counters).
-template <typename Draws, int kMinBlocks, bool kInstr>
-__global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a) {
-  // The displacement accumulator and the position at the start of the step are only touched when a time step ends;
-  // they live in shared memory (one slot per thread) so that the event path does not carry 12 registers of them.
-  __shared__ double s_delta[3][128], s_old[3][128];
+template <typename Draws, bool kInstr, int G>
+__device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3][128], double (&s_old)[3][128], const int lane_block) {
+  typedef typename LoopDraws<Draws, G>::type DrawsT;
   const int      tid = threadIdx.x, lane = threadIdx.x & 31;
+  const int      gbase = lane & ~(G - 1);
+  const bool     leader = (lane == gbase);
   const unsigned lt_mask = (1u << lane) - 1u;
-  const bool     hot_role = (int)blockIdx.x < a.hot_blocks;
+  const bool     hot_role = lane_block < a.hot_blocks;
+  const bool     deep_on = a.deep_blocks > 0;
   uint32_t       e = 0;
   Lane           L{};
-  Draws          D{};
+  DrawsT         D{};
   double         dt_rem = 0.0;
   int32_t        step = 0;
   int32_t*       trace = nullptr;
   int32_t        trace_base = 0;  // events already in the exciton's trace when the current time step began
+  int32_t        waited = 0;      // iterations this lane's operation has been parked
   unsigned long long t_enter = 0, it_busy = 0, it_idle = 0, t_dry = 0;
   int                iter = 0;
   if (kInstr) t_enter = global_ns();
 #if defined(CNTMC_PROFILE_SEGMENTS)
   L.seg_t = clock64();
 #endif
+  const bool resume = (G > 1) && a.pass == 2;  // the excitons of this pass come with a cursor
+  const bool park = (G == 1) && (a.park_min_s > 1 || a.park_min_e > 1);
 
   auto start = [&]() {
     const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject, nf = L.nfast;
@@ -246,88 +354,139 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
     init_draws(D, a.draws, a.S, (int64_t)e);
     step = 0;
     dt_rem = a.dt;
+    waited = 0;
     s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
     s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;  // _old_pos = _pos (particle.cpp:59)
+    if (resume) {
+      step = a.C.step[e];
+      dt_rem = a.C.dt_rem[e];
+      L.nevent = a.C.nevent[e];
+      s_old[0][tid] = a.C.ox[e]; s_old[1][tid] = a.C.oy[e]; s_old[2][tid] = a.C.oz[e];
+    }
     if (kInstr && a.trace_sites) {  // the trace continues where the previous launch stopped
-      trace_base = a.trace_counts[e];
-      trace = a.trace_sites + (int64_t)e * a.trace_cap + trace_base;
+      trace_base = a.trace_counts[e];  // may exceed the capacity: events beyond it are counted, not recorded
+      trace = (leader && trace_base < a.trace_cap) ? a.trace_sites + (int64_t)e * a.trace_cap + trace_base : nullptr;
     }
   };
   // A warp keeps to one role so that its lanes run the same branch of the loop most of the time (hot: scattering
   // events, cold: chain walks and step ends); it changes role only once, when all its lanes have run dry.
-  bool role = hot_role;
-  for (int pass = 0; pass < 2; ++pass, role = !role) {
-    int64_t e64 = 0;
-    bool    have = take_exciton(a.q, true, role, lane, lt_mask, e64);
+  // the lists a warp serves in its first and in its second role, four bits per list number
+  const uint32_t hot_lists = deep_on ? 0x23u : 0x234u, cold_lists = 0x10u;
+  const int      n_hot = deep_on ? 2 : 3, n_roles = (G > 1) ? 1 : 2;
+  for (int role = 0; role < n_roles; ++role) {
+    const bool     serve_hot = (role == 0) == hot_role;
+    const uint32_t serve = (G > 1) ? (a.pass == 2 ? (uint32_t)kDeferred : 4u) : serve_hot ? hot_lists : cold_lists;
+    const int      n_serve = (G > 1) ? 1 : serve_hot ? n_hot : 2;
+    int64_t        e64 = 0;
+    bool           have = take_exciton(a.q, leader, serve, n_serve, lane, lt_mask, e64);
+    if (G > 1) {
+      have = __shfl_sync(kFullMask, have ? 1 : 0, gbase) != 0;
+      e64 = __shfl_sync(kFullMask, e64, gbase);
+    }
     if (have) {
       e = (uint32_t)e64;
       start();
     }
     while (__any_sync(kFullMask, have)) {
-      bool finished = false;
+      bool finished = false, did_event = false;
       if (kInstr) {
         if (have) ++it_busy; else ++it_idle;
         ++iter;
       }
       // One iteration = up to two operations per lane: first the end of a time step for the lanes whose free flight
       // outlasts the step, then a scattering event for the lanes whose flight ends inside the (possibly new) step.
-      // The warp pays the latency of both code paths anyway whenever both kinds are present, so a lane that ends a
-      // step and scatters right away gets both done in the same pass.
+      const bool need_s = have && !(L.ff <= dt_rem);  // particle.cpp:62 false: the flight outlasts the step
+      bool       run_s = true, run_e = true;
+      if (park) {
+        const int  n_s = __popc(__ballot_sync(kFullMask, need_s)), n_e = __popc(__ballot_sync(kFullMask, have && !need_s));
+        const bool old = __any_sync(kFullMask, have && waited >= a.park_age);
+        run_s = n_s > 0 && (n_s >= a.park_min_s || n_e == 0 || old);
+        run_e = n_e > 0 && (n_e >= a.park_min_e || n_s == 0 || old);
+        if (!run_s && !run_e) {
+          run_s = n_s >= n_e;
+          run_e = !run_s;
+        }
+      }
       CNTMC_SEG(L, 6);  // loop head, refill
-      if (have && !(L.ff <= dt_rem)) {  // particle.cpp:62 false: the flight outlasts the step
+      if (need_s && run_s) {
         const double t = dt_rem;
         const Leg    leg = fly(L, a.T, t, true);
         L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
         after_flight_step_end(L, a.T, D, leg, t, s_old[0][tid], s_old[1][tid], s_old[2][tid]);
-        // streaming stores: written once, read once by the reduction, must not evict the tables from L2
-        double2* rec = reinterpret_cast<double2*>(a.stage + ((size_t)step * (size_t)a.P + (size_t)e));
-        __stcs(rec, make_double2(L.dx * L.dx, L.dy * L.dy));  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
-        __stcs(rec + 1, make_double2(L.dz * L.dz, (double)L.nevent));  // events of this time step
+        if (leader) {
+          // streaming stores: written once, read once by the reduction, must not evict the tables from L2
+          double2* rec = reinterpret_cast<double2*>(a.stage + ((size_t)step * (size_t)a.P + (size_t)e));
+          __stcs(rec, make_double2(L.dx * L.dx, L.dy * L.dy));  // std::pow(delta_pos, 2), monte_carlo.cpp:397-399
+          __stcs(rec + 1, make_double2(L.dz * L.dz, (double)L.nevent));  // events of this time step
+        }
         s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
         s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;
         ++step;
         dt_rem = a.dt;
         if (kInstr) {
           trace_base += (int32_t)L.nevent;
-          if (trace) trace += L.nevent;
+          if (trace) trace = (trace_base < a.trace_cap) ? trace + L.nevent : nullptr;
         }
         L.nevent = 0;
+        waited = 0;
         finished = (step >= a.nsteps);
       }
       CNTMC_SEG(L, 5);  // step-end path (own, or waiting for the lanes that run it)
-      if (have && !finished && (L.ff <= dt_rem)) {
+      const bool need_e = have && !finished && (L.ff <= dt_rem);
+      if (need_e && run_e) {
         const double t = L.ff;
         const Leg    leg = fly(L, a.T, t, false);
         dt_rem -= t;  // particle.cpp:63
-        after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, kInstr ? (uint32_t)(a.trace_cap - trace_base) : 0u, a.top_entries != 0);
+        const uint32_t room = (kInstr && trace) ? (uint32_t)(a.trace_cap - trace_base) : 0u;
+        after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, room, a.top_entries != 0);
+        did_event = true;
+        waited = 0;
       }
+      if (park && have && !finished && ((need_s && !run_s) || (need_e && !run_e))) ++waited;
       CNTMC_SEG(L, 7);  // waiting for the other lanes of the warp to finish their events
       finished = have && (finished || L.stuck);
-      if (__any_sync(kFullMask, finished)) {
+      // landed in a deep trap: the group solver takes over (lane blocks only)
+      const bool defer = (G == 1) && deep_on && did_event && !finished && L.hop_valid && L.hop.total >= a.deep_rate;
+      const bool release = finished || defer;
+      if (__any_sync(kFullMask, release)) {
         int cls = 0;
-        if (finished) {
+        if (release) {
           materialize(L, a.T);
           L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
-          store_lane(L, a.S, (int64_t)e);
-          cls = activity_class(hop_info(L, a.T).total * a.dt);
-          if (kInstr && a.trace_counts) a.trace_counts[e] = trace_base + (int32_t)L.nevent;
-          if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
-          if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
+          if (leader) {
+            store_lane(L, a.S, (int64_t)e);
+            if (defer) {
+              a.C.step[e] = step;
+              a.C.dt_rem[e] = dt_rem;
+              a.C.nevent[e] = L.nevent;
+              a.C.ox[e] = s_old[0][tid]; a.C.oy[e] = s_old[1][tid]; a.C.oz[e] = s_old[2][tid];
+            }
+            if (kInstr && a.trace_counts) a.trace_counts[e] = trace_base + (defer ? 0 : (int32_t)L.nevent);
+            if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
+            if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
+          }
+          if (finished) cls = activity_class(hop_info(L, a.T).total * a.dt, a.deep_thr);
         }
-        file_excitons(a.q, finished, cls, e, lane, lt_mask);
-        const bool got = take_exciton(a.q, finished, role, lane, lt_mask, e64);
-        if (finished) {
+        file_excitons(a.q, finished && leader, cls, e, lane, lt_mask);
+        if (G == 1 && deep_on) defer_excitons(a.q, defer, e, lane, lt_mask);
+        bool got = take_exciton(a.q, release && leader, serve, n_serve, lane, lt_mask, e64);
+        if (G > 1) {
+          got = __shfl_sync(kFullMask, got ? 1 : 0, gbase) != 0;
+          e64 = __shfl_sync(kFullMask, e64, gbase);
+        }
+        if (release) {
           have = got;
           if (have) {
             e = (uint32_t)e64;
             start();
           }
         }
-        if (kInstr && t_dry == 0 && __any_sync(kFullMask, finished && !got)) t_dry = global_ns();
+        if (kInstr && t_dry == 0 && __any_sync(kFullMask, release && !got)) t_dry = global_ns();
       }
     }
   }
 
+  if (!leader) L.nreinject = L.ncross = L.nprobe = L.nfast = 0;  // the lanes of a group counted the same things
   const unsigned nr = __reduce_add_sync(kFullMask, L.nreinject);
   if (lane == 0 && nr) atomicAdd(a.counters + CTR_REINJECT, (unsigned long long)nr);
   if (kInstr) {
@@ -350,7 +509,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
         w[0] = t_enter;
         w[1] = t_dry ? t_dry : t_exit;
         w[2] = t_exit;
-        w[3] = (hot_role ? 1ull : 0ull) | ((unsigned long long)iter << 8);
+        w[3] = (G > 1 ? 2ull : hot_role ? 1ull : 0ull) | ((unsigned long long)iter << 8);
 #if defined(CNTMC_PROFILE_SEGMENTS)
         for (int k = 0; k < 8; ++k) w[4 + k] = (unsigned long long)L.seg[k];  // lane 0 of the warp
 #endif
@@ -359,14 +518,38 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
   }
 }
 
+constexpr int kGroup = 8;  // lanes per exciton in the group solver
+template <typename Draws>
+struct SupportsGroups {
+  static constexpr bool value = false;
+};
+template <>
+struct SupportsGroups<PhiloxDraws> {
+  static constexpr bool value = true;
+};
+
+template <typename Draws, int kMinBlocks, bool kInstr>
+__global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a) {
+  // The displacement accumulator and the position at the start of the step are only touched when a time step ends;
+  // they live in shared memory (one slot per thread) so that the event path does not carry 12 registers of them.
+  __shared__ double s_delta[3][128], s_old[3][128];
+  if constexpr (SupportsGroups<Draws>::value) {
+    if (a.pass == 2 || (int)blockIdx.x < a.deep_blocks) {
+      hop_loop<Draws, kInstr, kGroup>(a, s_delta, s_old, 0);
+      return;
+    }
+  }
+  hop_loop<Draws, kInstr, 1>(a, s_delta, s_old, (int)blockIdx.x - a.deep_blocks);
+}
+
 
 // file every exciton under its activity class (first launch after creation or after an upload of the population)
-__global__ void __launch_bounds__(256) classify_kernel(const Tables T, const int32_t* site, int64_t P, double dt, ClassLists q) {
+__global__ void __launch_bounds__(256) classify_kernel(const Tables T, const int32_t* site, int64_t P, double dt, double deep_thr, ClassLists q) {
   const int64_t  e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int      lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const bool     mine = e < P;
-  const int      cls = mine ? activity_class(load_hop(T.site + site[e]).total * dt) : 0;
+  const int      cls = mine ? activity_class(load_hop(T.site + site[e]).total * dt, deep_thr) : 0;
   file_excitons(q, mine, cls, (uint32_t)e, lane, lt_mask);
 }
 
@@ -562,7 +745,6 @@ __global__ void __launch_bounds__(256) create_contact_population_kernel(const Co
   init_draws(D, a.draws, a.S, e);
   create_exciton(L, a.T, D, a.slab_sites + a.site_off[slab], (int32_t)(a.site_off[slab + 1] - a.site_off[slab]));
   store_lane(L, a.S, e);
-  a.S.last_events[e] = 0;
   a.alive[e] = 1;
   if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
 }

@@ -193,9 +193,10 @@ class monte_carlo:
                 f.write("%.6e,%.6e,%d,%.6e\n" % (ymin + (i + 0.5) * dy, float(n) / float(total), n, float(n) / (a * dy)))
 
     def track_particle(self, dt: float, file_no: int, max_steps: int = 1 << 20) -> bool:
-        """monte_carlo.h:786-818: particle_path.<file_no>.dat; the exciton's stream is (seed, file_no).  Returns whether
+        """monte_carlo.h:786-818: particle_path.<file_no>.dat; the exciton's stream is (seed, 2^63 | file_no), a
+        domain of its own (never the draws of exciton file_no of the population).  Returns whether
         the last slab was reached within max_steps (the reference's loop is unbounded)."""
-        path, reached = self._engine.track_particle(dt, seed=self._seed, global_id=file_no, max_steps=max_steps)
+        path, reached = self._engine.track_particle(dt, seed=self._seed, global_id=(1 << 63) | file_no, max_steps=max_steps)
         with open(os.path.join(self._output_directory, "particle_path.%d.dat" % file_no), "w") as f:
             for r in path:
                 f.write("   %+.6e %+.6e %+.6e\n" % tuple(r))

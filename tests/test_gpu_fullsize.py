@@ -48,7 +48,7 @@ def test_full_size_properties(c2):
     # the tube ends -- 100 sites x 5 nm against 20 nm of flight per step -- and it may shrink again)
     assert np.all(np.diff(msd.sum(axis=1)[:12]) > 0) and np.all(msd > 0)
     # launch size, scheduling options and splitting the call change nothing, bit for bit
-    e2, _, q1, msd2 = run(c2, dict(chunk_steps=16, hot_pct=0, occupancy=6), steps=(5, STEPS - 5))
+    e2, _, q1, msd2 = run(c2, dict(chunk_steps=16, hot_pct=0, occupancy=6, deep_thr=0), steps=(5, STEPS - 5))
     assert all(np.array_equal(p1[k], q1[k]) for k in p1)
     assert np.array_equal(msd, msd2) and e2.hops() == e.hops()
     # a shard of the population run alone follows the same trajectories (what multi-GPU sharding relies on)
