@@ -70,6 +70,24 @@ SIGNATURES = {
     "cntmc_sync": (C.c_int, [V]),
     "cntmc_last_kernel_ms": (D, [V]),
     "cntmc_last_kernel_launches": (I64, [V]),
+    "cntmc_multi_create": (C.c_int, [CP, C.c_int, V, C.POINTER(V)]),
+    "cntmc_multi_destroy": (None, [V]),
+    "cntmc_multi_last_error": (CP, [V]),
+    "cntmc_multi_num_devices": (C.c_int, [V]),
+    "cntmc_multi_handle": (V, [V, C.c_int]),
+    "cntmc_multi_nccl_version": (C.c_int, []),
+    "cntmc_multi_load_mesh": (C.c_int, [V, CP]),
+    "cntmc_multi_set_mesh": (C.c_int, [V, I64, I64, V, V]),
+    "cntmc_multi_set_option": (C.c_int, [V, CP, I64]),
+    "cntmc_multi_kubo_init": (C.c_int, [V]),
+    "cntmc_multi_kubo_create_particles": (C.c_int, [V, I64, U64]),
+    "cntmc_multi_kubo_step": (C.c_int, [V, D, I64, V]),
+    "cntmc_multi_get_particles": (C.c_int, [V, V, V, V, V, V, V]),
+    "cntmc_multi_number_of_particles": (I64, [V]),
+    "cntmc_multi_hops": (I64, [V]),
+    "cntmc_multi_time": (D, [V]),
+    "cntmc_multi_init": (C.c_int, [V, I64, I64, U64]),
+    "cntmc_multi_step": (C.c_int, [V, D, I64, V, V]),
 }
 
 _lib = None

@@ -17,8 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 CPP = os.path.join(HERE, "cpp")
 LIB = os.path.join(HERE, "libcntmc.so")
 DRIVER = os.path.join(HERE, "cntmc_main")
-SOURCES = ["cntmc_api.cu", "host_setup.cpp"]
-HEADERS = ["hop_core.h", "csr_core.h", "kernels.cuh", "host_setup.h", "json_min.h"]
+SOURCES = ["cntmc_api.cu", "cntmc_multi.cu", "host_setup.cpp"]
+HEADERS = ["hop_core.h", "fast_log.h", "log_table.inc", "csr_core.h", "kernels.cuh", "host_setup.h", "json_min.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
@@ -40,7 +40,7 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or needs_build():
-        cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+        cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
@@ -51,7 +51,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 def build_segments() -> str:
     """Diagnostics build with per-segment cycle counters in the hop loop (tools/segments.py): libcntmc_seg.so."""
     out = os.path.join(HERE, "libcntmc_seg.so")
-    subprocess.check_call([NVCC, *FLAGS, "-DCNTMC_PROFILE_SEGMENTS", "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]])
+    subprocess.check_call([NVCC, *FLAGS, "-DCNTMC_PROFILE_SEGMENTS", "-o", out, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"])
+    return out
+
+
+def build_variant(name: str, *defines: str) -> str:
+    """A/B builds for kernel experiments (tools/gpu_*.sh select them with CNTMC_LIB=...): libcntmc_<name>.so."""
+    out = os.path.join(HERE, "libcntmc_%s.so" % name)
+    subprocess.check_call([NVCC, *FLAGS, *["-D" + d for d in defines], "-o", out, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"])
     return out
 
 

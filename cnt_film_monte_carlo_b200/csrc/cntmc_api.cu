@@ -188,8 +188,9 @@ struct cntmc_handle {
   int64_t opt_runs = 1;         // chain walks over memory-consecutive sites read segment times instead of chasing records
   int64_t opt_top_entries = 1;  // the three widest entries of a row are tried before the row is searched
   int64_t opt_hot_pct = 30;   // share of the lane blocks that serve the most active classes first
+  int64_t opt_gid_base = 0;   // contact mode: stream ids start at opt_gid_base * 2^56 (cntmc_multi gives every GPU its own range)
   int64_t opt_deep_thr = 16;  // Gamma*dt from which an exciton belongs to the group solver (0: no group solver)
-  int64_t opt_deep_pct = 20;  // share of the blocks that run the group solver in the first pass of a launch
+  int64_t opt_deep_blocks = 4;  // blocks per SM of the trap solver's launch
   int64_t opt_park_min_s = 1, opt_park_min_e = 1, opt_park_age = 4;  // parking of the minority operation in lane blocks
   int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
   int64_t opt_stage_mb = 0;  // cap on the (step, exciton) staging buffer in MiB; shortens the launches if needed.
@@ -516,7 +517,7 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   }
   h->d_list_head.alloc(kLists);
   // group solver (counter-based streams only: a replayed stream has nothing to prepare in parallel)
-  const bool   deep = h->opt_deep_thr > 0 && h->opt_deep_pct > 0 && !h->replay;
+  const bool   deep = h->opt_deep_thr > 0 && !h->replay;
   const double deep_thr = deep ? (double)h->opt_deep_thr : INFINITY;
   h->d_defer_list.alloc((size_t)h->P);
   h->d_defer_count.alloc(1);
@@ -563,13 +564,11 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     a.C.nevent = h->d_cur_nevent.p;
     a.draws = h->draws;
     a.q = lists(h->cur_list);
-    a.pass = 1;
-    a.deep_blocks = deep ? std::max<int32_t>(1, (int32_t)((int64_t)grid * h->opt_deep_pct / 100)) : 0;
-    if (a.deep_blocks >= (int32_t)grid) a.deep_blocks = (int32_t)grid - 1;
-    if (a.deep_blocks < 0) a.deep_blocks = 0;
-    a.hot_blocks = (int32_t)(((int64_t)grid - a.deep_blocks) * h->opt_hot_pct / 100);
+    a.deep_on = deep ? 1 : 0;
+    a.n_sites = h->sites.N;
+    a.hot_blocks = (int32_t)((int64_t)grid * h->opt_hot_pct / 100);
     a.top_entries = (int32_t)h->opt_top_entries;
-    a.deep_thr = a.deep_blocks > 0 ? deep_thr : INFINITY;
+    a.deep_thr = deep_thr;
     a.deep_rate = a.deep_thr / dt;
     a.park_min_s = (int32_t)h->opt_park_min_s;
     a.park_min_e = (int32_t)h->opt_park_min_e;
@@ -591,12 +590,18 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
       h->kernel_events.push_back(k1);
       CUDA_CHECK(cudaEventRecord(k0, st));
     }
-    for (int pass = 1; pass <= (a.deep_blocks > 0 ? 2 : 1); ++pass) {
-      a.pass = pass;  // 2: the excitons the lane blocks deferred, all blocks run the group solver
-      if (h->replay)
-        launch_kubo<ReplayDraws>(h, a, grid, st);
+    if (h->replay)
+      launch_kubo<ReplayDraws>(h, a, grid, st);
+    else
+      launch_kubo<PhiloxDraws>(h, a, grid, st);
+    CUDA_CHECK(cudaGetLastError());
+    h->last_launches += 1;
+    if (deep) {  // the trap solver: class 4 and what the lanes deferred; blocks without work leave at once
+      const unsigned dgrid = (unsigned)((int64_t)h->sm_count * h->opt_deep_blocks);
+      if (h->trace_cap > 0 || h->opt_stats)
+        deep_kernel<true><<<dgrid, 128, 0, st>>>(a);
       else
-        launch_kubo<PhiloxDraws>(h, a, grid, st);
+        deep_kernel<false><<<dgrid, 128, 0, st>>>(a);
       CUDA_CHECK(cudaGetLastError());
       h->last_launches += 1;
     }
@@ -902,7 +907,7 @@ int cntmc_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_
     h->replay = false;
     h->draws = DrawConfig{};
     h->draws.seed = seed;
-    h->draws.first_gid = 0;
+    h->draws.first_gid = (uint64_t)h->opt_gid_base << 56;  // several handles of one simulation keep their stream ids apart
     // create_particles (monte_carlo.h:274-316): linear profile over the slabs, sites from the half-open slab lists
     const double         dp = double(c2_pop - c1_pop) / (double(n_seg) - 1);
     std::vector<int64_t> count_off((size_t)n_seg + 1, 0), site_off((size_t)n_seg + 1, 0);
@@ -920,7 +925,7 @@ int cntmc_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_
     h->capacity = 0;
     h->reserve_contact(std::max<int64_t>(capacity, P0 + 1), 0);
     h->P = P0;
-    h->next_gid = (uint64_t)P0;
+    h->next_gid = h->draws.first_gid + (uint64_t)P0;
     h->time = 0;
     h->hops = h->reinjections = h->crossings = h->probes = 0;
     if (P0 > 0) {
@@ -1288,12 +1293,15 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     if (k == "chunk_steps") {
       require(value >= 1 && value <= 256, "chunk_steps must be in [1, 256]");
       h->opt_chunk = value;
+    } else if (k == "gid_base_shift56") {
+      require(value >= 0 && value < 128, "gid_base_shift56 must be in [0, 128)");
+      h->opt_gid_base = value;
     } else if (k == "deep_thr") {
       require(value >= 0 && value <= 1000000, "deep_thr must be in [0, 1e6] (0 = no group solver)");
       h->opt_deep_thr = value;
-    } else if (k == "deep_pct") {
-      require(value >= 0 && value <= 90, "deep_pct must be in [0, 90]");
-      h->opt_deep_pct = value;
+    } else if (k == "deep_blocks") {
+      require(value >= 1 && value <= 4, "deep_blocks must be 1 to 4 blocks per SM");
+      h->opt_deep_blocks = value;
     } else if (k == "park_min_s" || k == "park_min_e") {
       require(value >= 1 && value <= 32, "park_min_* must be in [1, 32]");
       (k == "park_min_s" ? h->opt_park_min_s : h->opt_park_min_e) = value;
@@ -1332,7 +1340,7 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "occupancy") return h->opt_occupancy;
   if (k == "hot_pct") return h->opt_hot_pct;
   if (k == "deep_thr") return h->opt_deep_thr;
-  if (k == "deep_pct") return h->opt_deep_pct;
+  if (k == "deep_blocks") return h->opt_deep_blocks;
   if (k == "park_min_s") return h->opt_park_min_s;
   if (k == "park_min_e") return h->opt_park_min_e;
   if (k == "park_age") return h->opt_park_age;

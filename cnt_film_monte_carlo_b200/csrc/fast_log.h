@@ -31,6 +31,9 @@ static const LogRow h_log_tab[128] = {
 #undef CNTMC_LOG_ROW
 
 CNTMC_HD double fast_log_unit(double x) {
+#if defined(CNTMC_LIBM_LOG)  // A/B builds only: the library's logarithm
+  return log(x);
+#endif
   uint64_t ix;
 #if defined(__CUDA_ARCH__)
   ix = (uint64_t)__double_as_longlong(x);

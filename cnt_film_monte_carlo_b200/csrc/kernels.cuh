@@ -170,7 +170,7 @@ __device__ __forceinline__ void defer_excitons(const ClassLists& q, bool mine, u
 // whole warp).  Returns false for lanes left without work.
 // serve: list numbers, four bits each, first one in the low bits
 __device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, uint32_t serve, int n_serve, int lane, unsigned lt_mask,
-                                             int64_t& e) {
+                                             int64_t& e, int& from) {
   bool     got = false;
   unsigned need = __ballot_sync(0xffffffffu, want);
   for (int k = 0; k < n_serve && need; ++k) {
@@ -185,6 +185,7 @@ __device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, uin
       const int rank = __popc(need & lt_mask);
       if ((long long)rank < avail) {
         e = (int64_t)q.list[c][base + (unsigned long long)rank];
+        from = c;
         got = true;
       }
     }
@@ -214,9 +215,9 @@ struct KuboArgs {
   CursorArrays        C;
   DrawConfig          draws;
   ClassLists          q;
-  int32_t             pass;         // 1: every list of the launch; 2: the excitons deferred during pass 1 (all blocks run the group solver)
-  int32_t             deep_blocks;  // blocks [0, deep_blocks) run the group solver on class 4
-  int32_t             hot_blocks;   // of the lane blocks, the first hot_blocks serve the active classes first
+  int32_t             deep_on;      // class 4 and the excitons that land in a deep trap are left to deep_kernel
+  int32_t             hot_blocks;   // blocks [0, hot_blocks) serve the active classes first
+  int64_t             n_sites;
   int32_t             top_entries;  // try the three widest entries of a row before searching it
   double              deep_thr;     // Gamma*dt from which an exciton belongs to the group solver (inf: never)
   double              deep_rate;    // the same as a rate: deep_thr / dt
@@ -295,10 +296,10 @@ struct LoopDraws<Draws, 1> {
   typedef Draws type;
 };
 
-// The loop of the hop kernel.  Persistent warps; every group of G lanes owns one exciton at a time, carries it through
+// The loop of the hop kernels.  Persistent warps; every group of G lanes owns one exciton at a time, carries it through
 // the time steps of the launch, files it under its activity class for the next launch and takes another one.
 //
-// G = 1 (lane blocks): one exciton per lane.  The loop is flat: an iteration moves every busy lane forward by the end of
+// G = 1 (kubo_kernel): one exciton per lane.  The loop is flat: an iteration moves every busy lane forward by the end of
 // one time step and / or one scattering event; lanes of a warp are in general in different time steps of different
 // excitons.  Nothing in the loop needs a barrier or a floating-point atomic: when a lane ends a step it writes its
 // squared displacement to the (step, exciton) record, and reduce_stage_kernel sums the records in a fixed order
@@ -307,26 +308,36 @@ struct LoopDraws<Draws, 1> {
 //   each.  With park_min_s / park_min_e > 1 the path that fewer than that many lanes ask for is skipped (its lanes
 //   wait, at most park_age iterations) until enough lanes have gathered.
 //   Deferral: an exciton that lands in a deep trap (Gamma*dt >= deep_thr) would occupy its lane for thousands of
-//   sequential events while the other 31 idle at the end of the launch; the lane stores it with its cursor (step, time
-//   left, events of the step, start-of-step position) and a second pass of the group solver finishes its launch.
+//   sequential events while the other 31 idle at the end of the launch -- at 1e6 excitons that chain IS the launch
+//   time.  The lane stores it with its cursor (step, time left, events of the step, start-of-step position) and
+//   deep_kernel finishes its launch.
 //
-// G > 1 (group solver): the G lanes of a group hold the same exciton and execute the same instructions on the same
-// values; what they share is the work that does not depend on the event chain -- the draws and logarithms of the next
-// G events (GroupDraws).  A trapped exciton's events then cost a short chain each (flight compare, dice, top entries,
-// destination record, 1/Gamma times a prepared logarithm) instead of that plus Philox plus log, and at most 32/G
-// excitons diverge inside a warp instead of 32.  Results are the same bits: same draws, same arithmetic, same order.
+// G = 8 (deep_kernel, the trap solver): the G lanes of a group hold the same exciton and execute the same instructions
+// on the same values, and they split what does not depend on the event chain:
+//   * lane j prepares the two draws of the j-th event from now and the logarithm of its free-flight draw (GroupDraws);
+//   * lane j keeps the record of site b + j of a window of G consecutive sites around the exciton in registers (a trap
+//     is two to five neighbouring sites of one tube), and for each of the G prepared dice draws it evaluates what an
+//     event on ITS site would do: dice = Gamma_j * r / RAND_MAX against the three widest entries of its row ->
+//     destination, as an index into the window (4 bits per draw; 15 = not decided here);
+//   * the chain itself is then walked from those registers with shuffles: flight time of the segment ahead against the
+//     free-flight time (owner's q), the owner's 4-bit answer for this draw, the destination's 1/Gamma times the
+//     prepared logarithm.  About 90 cycles and 25 instructions per event instead of ~2000 and 200.
+// Whatever the walk cannot decide -- a flight that reaches the next site, a dice outside the top entries, a destination
+// outside the window, the end of a time step -- leaves the exciton exactly where the generic path (the same code as
+// G = 1, run redundantly by the G lanes) picks it up.  Same draws, same arithmetic, same order: the same bits.
 // Only the first lane of a group stores anything.
 //
 // kInstr adds what only tests and the roofline bookkeeping need (site traces, probe / crossing counters).
 template <typename Draws, bool kInstr, int G>
-__device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3][128], double (&s_old)[3][128], const int lane_block) {
+__device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3][128], double (&s_old)[3][128]) {
   typedef typename LoopDraws<Draws, G>::type DrawsT;
   const int      tid = threadIdx.x, lane = threadIdx.x & 31;
   const int      gbase = lane & ~(G - 1);
   const bool     leader = (lane == gbase);
   const unsigned lt_mask = (1u << lane) - 1u;
-  const bool     hot_role = lane_block < a.hot_blocks;
-  const bool     deep_on = a.deep_blocks > 0;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+  const bool     hot_role = (int)blockIdx.x < a.hot_blocks;
+  const bool     deep_on = a.deep_on != 0;
   uint32_t       e = 0;
   Lane           L{};
   DrawsT         D{};
@@ -335,14 +346,19 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
   int32_t*       trace = nullptr;
   int32_t        trace_base = 0;  // events already in the exciton's trace when the current time step began
   int32_t        waited = 0;      // iterations this lane's operation has been parked
+  int            from = 0;        // the list the current exciton came from
   unsigned long long t_enter = 0, it_busy = 0, it_idle = 0, t_dry = 0;
   int                iter = 0;
   if (kInstr) t_enter = global_ns();
 #if defined(CNTMC_PROFILE_SEGMENTS)
   L.seg_t = clock64();
 #endif
-  const bool resume = (G > 1) && a.pass == 2;  // the excitons of this pass come with a cursor
   const bool park = (G == 1) && (a.park_min_s > 1 || a.park_min_e > 1);
+  // trap solver: this lane's site of the window
+  int32_t  win_b = -1;
+  double   w_total = 0, w_inv = 0, w_lo0 = 0, w_hi0 = 0, w_lo1 = 0, w_hi1 = 0, w_lo2 = 0, w_hi2 = 0, w_qr = 0, w_ql = 0;
+  int32_t  w_n0 = -1, w_n1 = -1, w_n2 = -1, w_left = -1, w_right = -1;
+  uint32_t w_rowlen = 0, w_flags = 0;
 
   auto start = [&]() {
     const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject, nf = L.nfast;
@@ -357,7 +373,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
     waited = 0;
     s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
     s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;  // _old_pos = _pos (particle.cpp:59)
-    if (resume) {
+    if (G > 1 && from == kDeferred) {  // handed over in the middle of a time step
       step = a.C.step[e];
       dt_rem = a.C.dt_rem[e];
       L.nevent = a.C.nevent[e];
@@ -370,18 +386,19 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
   };
   // A warp keeps to one role so that its lanes run the same branch of the loop most of the time (hot: scattering
   // events, cold: chain walks and step ends); it changes role only once, when all its lanes have run dry.
-  // the lists a warp serves in its first and in its second role, four bits per list number
+  // The lists a warp serves in its first and in its second role, four bits per list number:
   const uint32_t hot_lists = deep_on ? 0x23u : 0x234u, cold_lists = 0x10u;
   const int      n_hot = deep_on ? 2 : 3, n_roles = (G > 1) ? 1 : 2;
   for (int role = 0; role < n_roles; ++role) {
     const bool     serve_hot = (role == 0) == hot_role;
-    const uint32_t serve = (G > 1) ? (a.pass == 2 ? (uint32_t)kDeferred : 4u) : serve_hot ? hot_lists : cold_lists;
-    const int      n_serve = (G > 1) ? 1 : serve_hot ? n_hot : 2;
+    const uint32_t serve = (G > 1) ? (4u | ((uint32_t)kDeferred << 4)) : serve_hot ? hot_lists : cold_lists;
+    const int      n_serve = (G > 1) ? 2 : serve_hot ? n_hot : 2;
     int64_t        e64 = 0;
-    bool           have = take_exciton(a.q, leader, serve, n_serve, lane, lt_mask, e64);
+    bool           have = take_exciton(a.q, leader, serve, n_serve, lane, lt_mask, e64, from);
     if (G > 1) {
       have = __shfl_sync(kFullMask, have ? 1 : 0, gbase) != 0;
       e64 = __shfl_sync(kFullMask, e64, gbase);
+      from = __shfl_sync(kFullMask, from, gbase);
     }
     if (have) {
       e = (uint32_t)e64;
@@ -392,6 +409,91 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
       if (kInstr) {
         if (have) ++it_busy; else ++it_idle;
         ++iter;
+      }
+      if constexpr (G > 1) {
+        // ---- trap solver: up to G events from the window registers (see the comment above hop_loop)
+        const bool can = have && L.at_site && (L.ff <= dt_rem) && a.top_entries != 0 && a.n_sites >= G;
+        if (can) {
+          if (win_b < 0 || L.site < win_b || L.site >= win_b + G) {  // (re)centre the window: lane j takes site b + j
+            int64_t b = (int64_t)L.site - (G / 2 - 1);
+            b = b < 0 ? 0 : (b > a.n_sites - G ? a.n_sites - G : b);
+            win_b = (int32_t)b;
+            const SiteRec*  rec = a.T.site + (win_b + (lane - gbase));
+            const SiteChain c = load_chain(rec);
+            const HopInfo   h = load_hop(rec);
+            const TopLoaded t = load_top(&rec->top);
+            w_left = c.left; w_right = c.right; w_qr = c.q_right; w_ql = c.q_left;
+            w_total = h.total; w_inv = h.inv_total; w_rowlen = h.row_len;
+            w_lo0 = t.lo0; w_hi0 = t.hi0; w_lo1 = t.lo1; w_hi1 = t.hi1; w_lo2 = t.lo2; w_hi2 = t.hi2;
+            w_n0 = t.nbr0; w_n1 = t.nbr1; w_n2 = t.nbr2;
+            // what particle::fly does with the heading on this site (particle.cpp:20-34): bit 0 = heading after a start
+            // to the right, bit 1 = after a start to the left, bit 2 = no chain neighbour at all (no motion)
+            w_flags = ((w_right > -1) ? 1u : 0u) | ((w_left > -1) ? 0u : 2u) | ((w_left < 0 && w_right < 0) ? 4u : 0u) |
+                      ((w_left == w_right) ? 4u : 0u);
+          }
+          uint32_t off = L.ndraw - D.nd0;
+          if (!D.valid || off >= 2u * G || (off & 1u)) {  // the prepared draws must start at an event
+            D.refill(L.ndraw);
+            off = 0;
+          }
+          const int k0 = (int)(off >> 1);
+          // every lane: what would an event on MY site do with each of the prepared dice draws?
+          uint32_t tbl = 0;
+          const int32_t my_site = win_b + (lane - gbase);
+#pragma unroll
+          for (int k = 0; k < G; ++k) {
+            const int32_t r = (int32_t)__shfl_sync(gmask, D.r1, gbase + k);
+            const double  dice = div_by(w_total * (double)r, kRandMax, kInvRandMax);  // scatterer.cpp:17
+            const bool    in0 = (w_lo0 <= dice) && (dice < w_hi0);
+            const bool    in1 = (w_lo1 <= dice) && (dice < w_hi1);
+            const bool    in2 = (w_lo2 <= dice) && (dice < w_hi2);
+            const int32_t dest = in0 ? w_n0 : in1 ? w_n1 : w_n2;
+            const int32_t di = dest - win_b;
+            const bool    ok = (in0 || in1 || in2) && w_rowlen != 0 && dest != my_site && di >= 0 && di < G;
+            tbl |= (ok ? (uint32_t)di : 15u) << (4 * k);
+          }
+          const unsigned zero2 = __ballot_sync(gmask, D.r2 == 0u) >> gbase;  // a zero free-flight draw is redrawn (scatterer.h:76-78)
+          int      s_idx = L.site - win_b;
+          bool     heading = L.heading_right, moved = false;
+          double   ff = L.ff;
+          const uint32_t room = (kInstr && trace) ? (uint32_t)(a.trace_cap - trace_base) : 0u;
+          for (int k = k0; k < G; ++k) {
+            if (!(ff <= dt_rem)) break;  // the flight outlasts the step
+            const uint32_t fl = __shfl_sync(gmask, w_flags, gbase + s_idx);
+            const double   qr = __shfl_sync(gmask, w_qr, gbase + s_idx), ql = __shfl_sync(gmask, w_ql, gbase + s_idx);
+            const uint32_t tb = __shfl_sync(gmask, tbl, gbase + s_idx);
+            const bool     still = (fl & 4u) != 0;  // link-less site: particle::fly returns at once (particle.cpp:11-12)
+            const bool     nh = heading ? (fl & 1u) != 0 : (fl & 2u) != 0;
+            const double   q = nh ? qr : ql;
+            if (still || q < ff) break;  // link-less or odd chains, and flights that reach the next site: generic path
+            const uint32_t di = (tb >> (4 * k)) & 15u;
+            if (di == 15u || ((zero2 >> k) & 1u)) break;
+            // event k: the flight stops on the way (its leg is never seen), the exciton hops to window site di
+            heading = nh;
+            dt_rem -= ff;  // particle.cpp:63
+            const double inv = __shfl_sync(gmask, w_inv, gbase + (int)di), lgk = __shfl_sync(gmask, D.lg, gbase + k);
+            ff = -inv * lgk;  // scatterer.h:79
+            s_idx = (int)di;
+            if (kInstr && trace != nullptr && L.nevent < room) trace[L.nevent] = win_b + s_idx;
+            ++L.nevent;
+            L.ndraw += 2u;
+            L.nprobe += 2u;
+            ++L.nfast;
+            moved = true;
+          }
+          if (moved) {
+            L.site = win_b + s_idx;
+            L.heading_right = heading;
+            L.ff = ff;
+            L.left = __shfl_sync(gmask, w_left, gbase + s_idx);
+            L.right = __shfl_sync(gmask, w_right, gbase + s_idx);
+            L.q_right = __shfl_sync(gmask, w_qr, gbase + s_idx);
+            L.q_left = __shfl_sync(gmask, w_ql, gbase + s_idx);
+            L.at_site = true;
+            L.pos_valid = false;
+            L.hop_valid = false;
+          }
+        }
       }
       // One iteration = up to two operations per lane: first the end of a time step for the lanes whose free flight
       // outlasts the step, then a scattering event for the lanes whose flight ends inside the (possibly new) step.
@@ -445,7 +547,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
       if (park && have && !finished && ((need_s && !run_s) || (need_e && !run_e))) ++waited;
       CNTMC_SEG(L, 7);  // waiting for the other lanes of the warp to finish their events
       finished = have && (finished || L.stuck);
-      // landed in a deep trap: the group solver takes over (lane blocks only)
+      // landed in a deep trap: the trap solver takes over
       const bool defer = (G == 1) && deep_on && did_event && !finished && L.hop_valid && L.hop.total >= a.deep_rate;
       const bool release = finished || defer;
       if (__any_sync(kFullMask, release)) {
@@ -469,10 +571,11 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
         }
         file_excitons(a.q, finished && leader, cls, e, lane, lt_mask);
         if (G == 1 && deep_on) defer_excitons(a.q, defer, e, lane, lt_mask);
-        bool got = take_exciton(a.q, release && leader, serve, n_serve, lane, lt_mask, e64);
+        bool got = take_exciton(a.q, release && leader, serve, n_serve, lane, lt_mask, e64, from);
         if (G > 1) {
           got = __shfl_sync(kFullMask, got ? 1 : 0, gbase) != 0;
           e64 = __shfl_sync(kFullMask, e64, gbase);
+          from = __shfl_sync(kFullMask, from, gbase);
         }
         if (release) {
           have = got;
@@ -504,12 +607,12 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
       atomicMax(a.counters + CTR_T_FIRST_INV, ~t_enter);
       atomicMax(a.counters + CTR_T_LAST, t_exit);
       atomicAdd(a.counters + CTR_WARPS, 1ULL);
-      if (a.warp_times) {
+      if (a.warp_times && G == 1) {
         unsigned long long* w = a.warp_times + kWarpTimeCols * ((size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5));
         w[0] = t_enter;
         w[1] = t_dry ? t_dry : t_exit;
         w[2] = t_exit;
-        w[3] = (G > 1 ? 2ull : hot_role ? 1ull : 0ull) | ((unsigned long long)iter << 8);
+        w[3] = (hot_role ? 1ull : 0ull) | ((unsigned long long)iter << 8);
 #if defined(CNTMC_PROFILE_SEGMENTS)
         for (int k = 0; k < 8; ++k) w[4 + k] = (unsigned long long)L.seg[k];  // lane 0 of the warp
 #endif
@@ -518,28 +621,20 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
   }
 }
 
-constexpr int kGroup = 8;  // lanes per exciton in the group solver
-template <typename Draws>
-struct SupportsGroups {
-  static constexpr bool value = false;
-};
-template <>
-struct SupportsGroups<PhiloxDraws> {
-  static constexpr bool value = true;
-};
+constexpr int kGroup = 8;  // lanes per exciton in the trap solver
 
 template <typename Draws, int kMinBlocks, bool kInstr>
 __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a) {
   // The displacement accumulator and the position at the start of the step are only touched when a time step ends;
   // they live in shared memory (one slot per thread) so that the event path does not carry 12 registers of them.
   __shared__ double s_delta[3][128], s_old[3][128];
-  if constexpr (SupportsGroups<Draws>::value) {
-    if (a.pass == 2 || (int)blockIdx.x < a.deep_blocks) {
-      hop_loop<Draws, kInstr, kGroup>(a, s_delta, s_old, 0);
-      return;
-    }
-  }
-  hop_loop<Draws, kInstr, 1>(a, s_delta, s_old, (int)blockIdx.x - a.deep_blocks);
+  hop_loop<Draws, kInstr, 1>(a, s_delta, s_old);
+}
+// the trap solver: class 4 of the previous launch and the excitons kubo_kernel deferred in this one
+template <bool kInstr>
+__global__ void __launch_bounds__(128, 4) deep_kernel(const KuboArgs a) {
+  __shared__ double s_delta[3][128], s_old[3][128];
+  hop_loop<PhiloxDraws, kInstr, kGroup>(a, s_delta, s_old);
 }
 
 

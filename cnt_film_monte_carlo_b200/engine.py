@@ -272,3 +272,87 @@ class Engine:
         counts, sites = np.empty(P, np.int32), np.empty((P, self._trace_cap), np.int32)
         self._ck(self.L.cntmc_trace_get(self.h, _p(counts), _p(sites)))
         return counts, sites
+
+
+class MultiEngine:
+    """One simulation on several GPUs of one box (cntmc_multi_*, include/cntmc.h): tables replicated, excitons split by
+    global id, one NCCL all-reduce of the per-step rows per call -- all inside libcntmc.so, one host thread."""
+
+    def __init__(self, config, devices):
+        self.L = _lib.load()
+        text = config if isinstance(config, str) else json.dumps(config)
+        devs = np.ascontiguousarray(list(devices), np.int32)
+        m = C.c_void_p()
+        rc = self.L.cntmc_multi_create(text.encode(), len(devs), _p(devs), C.byref(m))
+        if rc != 0:
+            raise CntmcError(rc, self.L.cntmc_multi_last_error(None).decode())
+        self.m = m
+        self.n = len(devs)
+        self.n_seg = 0
+
+    def close(self):
+        if getattr(self, "m", None):
+            self.L.cntmc_multi_destroy(self.m)
+            self.m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise CntmcError(rc, self.L.cntmc_multi_last_error(self.m).decode())
+
+    def nccl_version(self) -> int:
+        return self.L.cntmc_multi_nccl_version()
+
+    def set_mesh(self, pos_nm: np.ndarray, orient: np.ndarray):
+        _, nt, nc = pos_nm.shape
+        p = np.ascontiguousarray(pos_nm.reshape(3, -1), np.float64)
+        o = np.ascontiguousarray(orient.reshape(3, -1), np.float64)
+        self._ck(self.L.cntmc_multi_set_mesh(self.m, nt, nc, _p(p), _p(o)))
+
+    def load_mesh(self, directory: Optional[str] = None):
+        self._ck(self.L.cntmc_multi_load_mesh(self.m, None if directory is None else directory.encode()))
+
+    def set_option(self, name: str, value: int):
+        self._ck(self.L.cntmc_multi_set_option(self.m, name.encode(), int(value)))
+
+    def kubo_init(self):
+        self._ck(self.L.cntmc_multi_kubo_init(self.m))
+
+    def kubo_create_particles(self, n: int = 0, seed: int = 1):
+        self._ck(self.L.cntmc_multi_kubo_create_particles(self.m, n, seed))
+
+    def kubo_step(self, dt: float, nsteps: int) -> np.ndarray:
+        msd = np.empty((nsteps, 3))
+        self._ck(self.L.cntmc_multi_kubo_step(self.m, dt, nsteps, _p(msd)))
+        return msd
+
+    def particles(self):
+        P = self.L.cntmc_multi_number_of_particles(self.m)
+        site, heading, ndraw = np.empty(P, np.int32), np.empty(P, np.uint8), np.empty(P, np.uint32)
+        pos, delta, ff = np.empty((3, P)), np.empty((3, P)), np.empty(P)
+        self._ck(self.L.cntmc_multi_get_particles(self.m, _p(site), _p(pos), _p(delta), _p(ff), _p(heading), _p(ndraw)))
+        return dict(site=site, pos=pos, delta=delta, ff=ff, heading=heading, ndraw=ndraw)
+
+    def hops(self) -> int:
+        return self.L.cntmc_multi_hops(self.m)
+
+    def time(self) -> float:
+        return self.L.cntmc_multi_time(self.m)
+
+    def number_of_particles(self) -> int:
+        return self.L.cntmc_multi_number_of_particles(self.m)
+
+    def init(self, c1_pop: int, c2_pop: int, seed: int = 1):
+        self._ck(self.L.cntmc_multi_init(self.m, c1_pop, c2_pop, seed))
+        self.n_seg = self.L.cntmc_number_of_segments(C.c_void_p(self.L.cntmc_multi_handle(self.m, 0)))
+
+    def step(self, dt: float, nsteps: int):
+        pop = np.empty((nsteps, self.n_seg), np.int64)
+        cur = np.empty((nsteps, self.n_seg - 1), np.int64)
+        self._ck(self.L.cntmc_multi_step(self.m, dt, nsteps, _p(pop), _p(cur)))
+        return pop, cur

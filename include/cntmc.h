@@ -9,7 +9,8 @@
  * Conventions: every function returning int gives 0 on success and a negative code on failure; the message is
  * available from cntmc_last_error(h) (or cntmc_last_error(NULL) when no handle exists yet).  No exception crosses the
  * boundary.  The caller owns every host buffer it passes; the handle owns all device memory.  One host thread per
- * handle; one handle drives one GPU.  All pointers are plain host pointers unless the name says "dev".
+ * handle; a cntmc_t drives one GPU, a cntmc_multi_t (end of this header) 1..8 GPUs of one box.  All pointers are
+ * plain host pointers unless the name says "dev".
  * There is no CPU execution path: without a CUDA device cntmc_kubo_init() fails with CNTMC_ERR_CUDA.
  */
 #ifndef CNTMC_H
@@ -162,7 +163,12 @@ int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites);
 
 /* ---- tuning (never changes results) ------------------------------------------------------------------------------------
  * chunk_steps  time steps per hop-kernel launch (default 64)          stage_mb     cap on the staging buffer in MiB (0 = auto)
- * hot_pct      share of the blocks that serve the most active excitons first (default 30)
+ * hot_pct      share of the lane blocks that serve the most active excitons first (default 30)
+ * deep_thr     Gamma*dt from which an exciton is handed to the trap solver (default 16; 0 = no trap solver)
+ * deep_blocks  blocks per SM of the trap solver's launch (default 4)
+ * park_min_s, park_min_e, park_age   lane blocks: the step-end / event path runs once that many lanes ask for it, or
+ *              after a lane has waited park_age iterations (defaults 1, 1, 4 = no parking)
+ * gid_base_shift56  contact mode: stream ids start at value * 2^56 (cntmc_multi keeps the GPUs' streams apart with it)
  * occupancy    resident 128-thread blocks per SM the hop kernel is compiled for (default 5)
  * top_entries  1: the three widest entries of a row are tried before the row is searched (default)
  * runs         1: chain walks over memory-consecutive sites read segment times instead of chasing records (default)
@@ -179,6 +185,40 @@ int cntmc_sync(cntmc_t* h);
 /* with option "time_kernels" = 1: summed device time and count of the hop-kernel launches of the last step call */
 double  cntmc_last_kernel_ms(const cntmc_t* h);
 int64_t cntmc_last_kernel_launches(const cntmc_t* h);
+
+/* ---- one simulation on several GPUs of one box ---------------------------------------------------------------------------
+ * The reference parallelises monte_carlo::kubo_step / step over its particle list with OpenMP (monte_carlo.cpp:320-338,
+ * monte_carlo.h:345-351).  A cntmc_multi_t does the same over GPUs: the read-only tables are replicated (each GPU
+ * builds its own neighbour table), the excitons are split by global id (the streams are keyed by global id, so every
+ * trajectory is the same bits for any number of GPUs), and each step call ends with ONE ncclAllReduce (sum) of the
+ * per-step rows -- the sums of kubo_save_avg_dispalcement_squared (monte_carlo.cpp:396-400) or the population / current
+ * bins (monte_carlo.h:566-573, 626-636) -- on every GPU's own stream.  NCCL is bound at run time (libnccl.so.2).
+ * One host thread; devices == NULL means GPUs 0..n_devices-1. */
+typedef struct cntmc_multi cntmc_multi_t;
+int  cntmc_multi_create(const char* json_text, int n_devices, const int* devices, cntmc_multi_t** out);
+void cntmc_multi_destroy(cntmc_multi_t* m);
+const char* cntmc_multi_last_error(const cntmc_multi_t* m);
+int  cntmc_multi_num_devices(const cntmc_multi_t* m);
+cntmc_t* cntmc_multi_handle(cntmc_multi_t* m, int i);     /* GPU i's own handle: read-backs, per-GPU options */
+int  cntmc_multi_nccl_version(void);                      /* ncclGetVersion of the library that was bound, -1 if none */
+int  cntmc_multi_load_mesh(cntmc_multi_t* m, const char* dir);                                   /* cntmc_load_mesh on every GPU */
+int  cntmc_multi_set_mesh(cntmc_multi_t* m, int64_t n_tubes, int64_t n_cols, const double* pos_nm, const double* orient);
+int  cntmc_multi_set_option(cntmc_multi_t* m, const char* name, int64_t value);
+int  cntmc_multi_kubo_init(cntmc_multi_t* m);                                                    /* monte_carlo::kubo_init */
+/* monte_carlo::kubo_create_particles: n_particles excitons in total, shard r = ids [first_r, first_r + n_r) */
+int  cntmc_multi_kubo_create_particles(cntmc_multi_t* m, int64_t n_particles, uint64_t seed);
+/* nsteps x { kubo_step ; kubo_save_avg_dispalcement_squared }: msd_out [nsteps][3] averaged over the WHOLE population */
+int  cntmc_multi_kubo_step(cntmc_multi_t* m, double dt, int64_t nsteps, double* msd_out);
+/* exciton state of the whole population in global-id order (arrays as cntmc_get_particles, P = all excitons) */
+int  cntmc_multi_get_particles(const cntmc_multi_t* m, int32_t* site, double* pos, double* delta, double* ff, uint8_t* heading,
+                               uint32_t* ndraw);
+int64_t cntmc_multi_number_of_particles(const cntmc_multi_t* m);
+int64_t cntmc_multi_hops(const cntmc_multi_t* m);
+double  cntmc_multi_time(const cntmc_multi_t* m);
+/* monte_carlo::init / step+save_metrics+repopulate_contacts with the contact populations split over the GPUs; bins
+ * summed over GPUs as in cntmc_step */
+int  cntmc_multi_init(cntmc_multi_t* m, int64_t c1_pop, int64_t c2_pop, uint64_t seed);
+int  cntmc_multi_step(cntmc_multi_t* m, double dt, int64_t nsteps, int64_t* pop_out, int64_t* curr_out);
 
 #ifdef __cplusplus
 }
