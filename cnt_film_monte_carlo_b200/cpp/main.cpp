@@ -1,7 +1,11 @@
 // cpp/main.cpp -- command-line driver, the counterpart of the reference's src/main.cpp (same CLI: argv[1] = input JSON,
 // default "input.json"; same "exciton monte carlo" block; same output files), running on libcntmc.so.
 //
-//   cntmc_main [input.json] [--steps-per-call N] [--seed S] [--contacts ITERATIONS [--c1 N] [--c2 N] [--track N]]
+//   cntmc_main [input.json] [--gpus N] [--steps-per-call N] [--seed S] [--displacements EVERY]
+//              [--contacts ITERATIONS [--c1 N] [--c2 N] [--track N]]
+//
+// --gpus N shards the excitons over GPUs 0..N-1 of the box (one NCCL all-reduce of the ensemble sums per engine call);
+// --displacements EVERY also writes particle_dispalcement.{x,y,z}.dat (monte_carlo.cpp:345-380) after every EVERY-th call.
 //
 // Without --contacts it runs the Green-Kubo loop of src/main.cpp:64-80.  With --contacts it runs ITERATIONS rounds of
 // the contact loop of src/main.cpp:98-106 (which the reference never reaches, and which never terminates there).
@@ -18,7 +22,8 @@ int main(int argc, char* argv[]) {
   std::cout << "\n***\nstart time:\n" << std::asctime(std::localtime(&start_time)) << "***\n\n";
 
   std::string filename = "input.json";
-  long long   steps_per_call = 1024, contact_iterations = -1, c1 = 1100, c2 = 0, n_track = 0, track_max_steps = 1 << 20;
+  long long   steps_per_call = 1024, contact_iterations = -1, c1 = 1100, c2 = 0, n_track = 0, track_max_steps = 1 << 20, n_gpus = 1,
+            displacements_every = 0;
   unsigned long long seed = 100;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -27,6 +32,8 @@ int main(int argc, char* argv[]) {
       return std::atoll(argv[++i]);
     };
     if (a == "--steps-per-call") steps_per_call = value("--steps-per-call");
+    else if (a == "--gpus") n_gpus = value("--gpus");
+    else if (a == "--displacements") displacements_every = value("--displacements");
     else if (a == "--seed") seed = (unsigned long long)value("--seed");
     else if (a == "--contacts") contact_iterations = value("--contacts");
     else if (a == "--c1") c1 = value("--c1");
@@ -47,7 +54,7 @@ int main(int argc, char* argv[]) {
     std::ostringstream block;
     cntmc::json::dump(j.at("exciton monte carlo"), block);
 
-    mc::monte_carlo sim(block.str());
+    mc::monte_carlo sim(block.str(), (int)n_gpus);
     sim.set_seed(seed);
     const double time_step = sim.time_step();
 
@@ -55,6 +62,7 @@ int main(int argc, char* argv[]) {
       sim.kubo_init();
       sim.save_json_properties();
       sim.kubo_create_particles();
+      long long calls = 0;
       while (sim.time() < sim.kubo_max_time()) {
         // how many more steps the reference's `while (time < max)` loop would take, with its own accumulation of _time
         double    t = sim.time();
@@ -64,11 +72,12 @@ int main(int argc, char* argv[]) {
           ++n;
         }
         sim.kubo_run(time_step, n);
+        if (displacements_every > 0 && (++calls % displacements_every) == 0) sim.kubo_save_individual_particle_dispalcements();
         std::cout << "kubo simulation: current time [seconds]: " << std::scientific << sim.time() << " .... "
                   << "max time [seconds]: " << sim.kubo_max_time() << "\r" << std::flush;
       }
       std::cout << std::endl << "Green-Kubo simulation finished!" << std::endl;
-      std::cout << "exciton hops: " << cntmc_hops(sim.handle()) << std::endl;
+      std::cout << "exciton hops: " << sim.hops() << std::endl;
     } else {
       sim.init(c1, c2);
       sim.save_json_properties();

@@ -61,9 +61,11 @@ inline fs::path check_directory(std::string path, bool should_be_empty = false) 
 class monte_carlo {
  private:
   cntmc_t*             _h = nullptr;
+  cntmc_multi_t*       _m = nullptr;  // more than one GPU: the same simulation sharded over the GPUs of the box (cntmc_multi_*)
   cntmc::json::Value   _json_prop;
   fs::path             _output_directory, _input_directory;
   std::fstream         _displacement_squard_file, _pop_file, _curr_file;
+  std::fstream         _displacement_file_x, _displacement_file_y, _displacement_file_z;
   std::vector<double>  _last_msd = std::vector<double>(3, 0.0);
   std::vector<int64_t> _last_pop, _last_curr;
   std::vector<double>  _area;
@@ -73,7 +75,7 @@ class monte_carlo {
 
   void ok(int rc) const {
     if (rc == CNTMC_OK) return;
-    const std::string msg = cntmc_last_error(_h);
+    const std::string msg = _m ? cntmc_multi_last_error(_m) : cntmc_last_error(_h);
     if (rc == CNTMC_ERR_INVALID) throw std::invalid_argument(msg);
     throw std::runtime_error(msg);
   }
@@ -83,22 +85,35 @@ class monte_carlo {
   monte_carlo(const monte_carlo&) = delete;
 
   // monte_carlo.h:116-136
-  explicit monte_carlo(const std::string& json_text) {
+  // n_gpus > 1: the excitons are split over GPUs 0..n_gpus-1 (the reference's OpenMP team over the particle list,
+  // monte_carlo.cpp:320-338, becomes one GPU per shard and one NCCL all-reduce of the ensemble sums per call)
+  explicit monte_carlo(const std::string& json_text, int n_gpus = 1) {
     std::cout << "\n" << "ready properties from json file" << "\n";
     _json_prop = cntmc::json::parse(json_text);
-    const int rc = cntmc_create(json_text.c_str(), &_h);
-    if (rc != CNTMC_OK) throw std::invalid_argument(cntmc_last_error(nullptr));
+    if (n_gpus > 1) {
+      if (cntmc_multi_create(json_text.c_str(), n_gpus, nullptr, &_m) != CNTMC_OK) throw std::invalid_argument(cntmc_multi_last_error(nullptr));
+      _h = cntmc_multi_handle(_m, 0);  // read-backs that are the same on every GPU (domain, sites, areas) use GPU 0's handle
+    } else {
+      const int rc = cntmc_create(json_text.c_str(), &_h);
+      if (rc != CNTMC_OK) throw std::invalid_argument(cntmc_last_error(nullptr));
+    }
     bool keep_old_data = true;
     if (const auto* v = _json_prop.find("keep old results")) keep_old_data = v->as_bool();
     _output_directory = prepare_directory(_json_prop.at("output directory").as_string(), keep_old_data);
     _input_directory = check_directory(_json_prop.at("mesh input directory").as_string(), false);
   }
-  ~monte_carlo() { cntmc_destroy(_h); }
+  ~monte_carlo() {
+    if (_m)
+      cntmc_multi_destroy(_m);
+    else
+      cntmc_destroy(_h);
+  }
 
-  double          time() const { return cntmc_time(_h); }                               // monte_carlo.h:139
+  double          time() const { return _m ? cntmc_multi_time(_m) : cntmc_time(_h); }   // monte_carlo.h:139
   const fs::path& output_path() const { return _output_directory; }                     // monte_carlo.h:148
   const fs::path& input_path() const { return _input_directory; }                       // monte_carlo.h:151
-  unsigned        number_of_particles() const { return (unsigned)cntmc_number_of_particles(_h); }  // monte_carlo.h:154
+  unsigned        number_of_particles() const { return (unsigned)(_m ? cntmc_multi_number_of_particles(_m) : cntmc_number_of_particles(_h)); }  // monte_carlo.h:154
+  int64_t         hops() const { return _m ? cntmc_multi_hops(_m) : cntmc_hops(_h); }
   double          kubo_max_time() const { return cntmc_kubo_max_time(_h); }             // monte_carlo.h:833
   double          time_step() const { return cntmc_time_step(_h); }
   cntmc_t*        handle() { return _h; }
@@ -114,8 +129,13 @@ class monte_carlo {
   // ---- Green-Kubo flavour ----------------------------------------------------------------------------------------------
   // monte_carlo.cpp:254-305
   void kubo_init() {
-    ok(cntmc_load_mesh(_h, _input_directory.string().c_str()));
-    ok(cntmc_kubo_init(_h));
+    if (_m) {
+      ok(cntmc_multi_load_mesh(_m, _input_directory.string().c_str()));
+      ok(cntmc_multi_kubo_init(_m));
+    } else {
+      ok(cntmc_load_mesh(_h, _input_directory.string().c_str()));
+      ok(cntmc_kubo_init(_h));
+    }
     ok(cntmc_get_domain(_h, _domain));
     int64_t n = 0;
     ok(cntmc_num_sites(_h, &n));
@@ -130,16 +150,38 @@ class monte_carlo {
     std::cout << "total number of scatterers: " << n << std::endl;
   }
   // monte_carlo.cpp:308-316
-  void kubo_create_particles() { ok(cntmc_kubo_create_particles(_h, 0, _seed, 0)); }
+  void kubo_create_particles() { ok(_m ? cntmc_multi_kubo_create_particles(_m, 0, _seed) : cntmc_kubo_create_particles(_h, 0, _seed, 0)); }
   // monte_carlo.cpp:319-342
-  void kubo_step(double dt) { ok(cntmc_kubo_step(_h, dt, 1, _last_msd.data())); }
+  void kubo_step(double dt) { ok(_m ? cntmc_multi_kubo_step(_m, dt, 1, _last_msd.data()) : cntmc_kubo_step(_h, dt, 1, _last_msd.data())); }
   // monte_carlo.cpp:382-409
   void kubo_save_avg_dispalcement_squared() { write_msd_rows(&_last_msd[0], 1, time(), 0.0); }
+  // monte_carlo.cpp:345-380: particle_dispalcement.{x,y,z}.dat, one column per exciton, one row per call
+  void kubo_save_individual_particle_dispalcements() {
+    const size_t        P = number_of_particles();
+    std::vector<double> delta(3 * P);
+    ok(_m ? cntmc_multi_get_particles(_m, nullptr, nullptr, delta.data(), nullptr, nullptr, nullptr)
+          : cntmc_get_particles(_h, nullptr, nullptr, delta.data(), nullptr, nullptr, nullptr));
+    std::fstream* files[3] = {&_displacement_file_x, &_displacement_file_y, &_displacement_file_z};
+    const char*   names[3] = {"particle_dispalcement.x.dat", "particle_dispalcement.y.dat", "particle_dispalcement.z.dat"};
+    for (int c = 0; c < 3; ++c) {
+      std::fstream& f = *files[c];
+      if (!f.is_open()) {
+        f.open((_output_directory / names[c]).string(), std::ios::out);
+        f << std::showpos << std::scientific;
+        f << "time";
+        for (int i = 0; i < int(P); ++i) f << "," << i;
+        f << std::endl;
+      }
+      f << time();
+      for (size_t i = 0; i < P; ++i) f << "," << delta[c * P + i];
+      f << std::endl;
+    }
+  }
   // nsteps x { kubo_step(dt); kubo_save_avg_dispalcement_squared(); } in one engine call; the rows are the same
   void kubo_run(double dt, int64_t nsteps) {
     std::vector<double> msd((size_t)nsteps * 3);
     const double        t0 = time();
-    ok(cntmc_kubo_step(_h, dt, nsteps, msd.data()));
+    ok(_m ? cntmc_multi_kubo_step(_m, dt, nsteps, msd.data()) : cntmc_kubo_step(_h, dt, nsteps, msd.data()));
     write_msd_rows(msd.data(), nsteps, t0, dt);
     for (int c = 0; c < 3; ++c) _last_msd[c] = msd[(size_t)(nsteps - 1) * 3 + c];
   }
@@ -147,8 +189,13 @@ class monte_carlo {
   // ---- contact flavour ---------------------------------------------------------------------------------------------------
   // monte_carlo.h:157-195 (contact populations 1100 and 0 are hard-coded there, :191-192)
   void init(int64_t c1_pop = 1100, int64_t c2_pop = 0) {
-    ok(cntmc_load_mesh(_h, _input_directory.string().c_str()));
-    ok(cntmc_init(_h, c1_pop, c2_pop, _seed, 0));
+    if (_m) {
+      ok(cntmc_multi_load_mesh(_m, _input_directory.string().c_str()));
+      ok(cntmc_multi_init(_m, c1_pop, c2_pop, _seed));
+    } else {
+      ok(cntmc_load_mesh(_h, _input_directory.string().c_str()));
+      ok(cntmc_init(_h, c1_pop, c2_pop, _seed, 0));
+    }
     _n_seg = (unsigned)cntmc_number_of_segments(_h);
     _area.resize(_n_seg);
     ok(cntmc_get_area(_h, _area.data()));
@@ -191,7 +238,9 @@ class monte_carlo {
   void save_scat_table() { ok(cntmc_save_rate_table(_h, _output_directory.string().c_str())); }
   void load_scat_table(const std::string& dir) { ok(cntmc_load_rate_table(_h, dir.c_str())); }
   // monte_carlo.h:343-355; the engine performs step, the counting of save_metrics and repopulate_contacts in one call
-  void step(double dt) { ok(cntmc_step(_h, dt, 1, _last_pop.data(), _last_curr.data())); }
+  void step(double dt) {
+    ok(_m ? cntmc_multi_step(_m, dt, 1, _last_pop.data(), _last_curr.data()) : cntmc_step(_h, dt, 1, _last_pop.data(), _last_curr.data()));
+  }
   // monte_carlo.h:519-522
   void save_metrics(double dt) {
     save_population_profile();
@@ -206,7 +255,7 @@ class monte_carlo {
       _displacement_squard_file.open((_output_directory / "particle_dispalcement.avg.squared.dat").string(), std::ios::out);
       _displacement_squard_file << std::showpos << std::scientific;
       _displacement_squard_file << "# this file contains the average of dx^2, dy^2, and dz^2 of the particle ensemble over time" << std::endl
-                                << "# number of particles: " << (size_t)cntmc_number_of_particles(_h) << std::endl
+                                << "# number of particles: " << (size_t)number_of_particles() << std::endl
                                 << std::endl;
       _displacement_squard_file << "time,x,y,z" << std::endl;
     }

@@ -12,6 +12,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <memory>
+#include <type_traits>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -165,7 +166,7 @@ struct cntmc_handle {
   // reductions, diagnostics
   DevBuf<double>             d_partial, d_sums;
   DevBuf<StageRec>           d_stage;
-  DevBuf<uint32_t>           d_list[2][kClasses], d_list_count[2], d_defer_list, d_defer_count;
+  DevBuf<uint32_t>           d_list[2][kClasses], d_list_count[2], d_hand_list[2], d_hand_count;  // hand-over lists: deferred, returned
   DevBuf<unsigned long long> d_list_head;
   DevBuf<double>             d_cur_dt, d_cur_ox, d_cur_oy, d_cur_oz;  // cursors of the excitons deferred to the group solver
   DevBuf<int32_t>            d_cur_step;
@@ -189,16 +190,18 @@ struct cntmc_handle {
   int64_t opt_top_entries = 1;  // the three widest entries of a row are tried before the row is searched
   int64_t opt_hot_pct = 30;   // share of the lane blocks that serve the most active classes first
   int64_t opt_gid_base = 0;   // contact mode: stream ids start at opt_gid_base * 2^56 (cntmc_multi gives every GPU its own range)
-  int64_t opt_deep_thr = 16;  // Gamma*dt from which an exciton belongs to the group solver (0: no group solver)
+  int64_t opt_deep_thr = 0;   // Gamma*dt from which an exciton belongs to the trap solver (0: no trap solver, the default:
+                              // parity-green but slower on every workload measured, profiles/round2_trap_solver.txt)
   int64_t opt_deep_blocks = 4;  // blocks per SM of the trap solver's launch
-  int64_t opt_park_min_s = 1, opt_park_min_e = 1, opt_park_age = 4;  // parking of the minority operation in lane blocks
+  int64_t opt_deep_rounds = 2;  // 2: the trap solver hands excitons that left their trap back to the lanes once per launch
   int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
   int64_t opt_stage_mb = 0;  // cap on the (step, exciton) staging buffer in MiB; shortens the launches if needed.
                              // 0 = a third of the device memory that is free when the buffer is first sized
   int     sm_count = 0;
   int64_t opt_stats = 0;         // count cumulative-rate probes and chain crossings (roofline bookkeeping)
   int64_t opt_time_kernels = 0;  // CUDA events around every hop-kernel launch (bench.py's roofline figure)
-  std::vector<cudaEvent_t> kernel_events;
+  std::vector<cudaEvent_t> kernel_events, deep_events;
+  double  deep_ms = 0;  // of kernel_ms, the part spent in the trap solver's launches
   double  kernel_ms = 0;
   int64_t kernel_launches = 0;
 
@@ -449,15 +452,21 @@ void create_common(cntmc_t* h, int64_t P) {
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 
 template <typename Draws, bool kInstr>
-void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) {
+void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st, bool defer) {
+  if constexpr (std::is_same<Draws, PhiloxDraws>::value) {
+    if (defer) {  // with the trap solver (one occupancy only: an opt-in path)
+      kubo_kernel<Draws, 5, kInstr, true><<<grid, 128, 0, st>>>(a);
+      return;
+    }
+  }
   switch (h->opt_occupancy) {
-    case 4: kubo_kernel<Draws, 4, kInstr><<<grid, 128, 0, st>>>(a); break;
-    case 6: kubo_kernel<Draws, 6, kInstr><<<grid, 128, 0, st>>>(a); break;
-    default: kubo_kernel<Draws, 5, kInstr><<<grid, 128, 0, st>>>(a); break;
+    case 4: kubo_kernel<Draws, 4, kInstr, false><<<grid, 128, 0, st>>>(a); break;
+    case 6: kubo_kernel<Draws, 6, kInstr, false><<<grid, 128, 0, st>>>(a); break;
+    default: kubo_kernel<Draws, 5, kInstr, false><<<grid, 128, 0, st>>>(a); break;
   }
 }
 template <typename Draws>
-void launch_kubo(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) {
+void launch_kubo(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st, bool defer) {
   // the instrumented variant (site traces, probe / crossing counters) runs only when somebody asked for its output
   if (h->trace_cap > 0 || h->opt_stats) {
     // the residency counters describe the last instrumented launch only
@@ -470,7 +479,7 @@ void launch_kubo(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) 
       d_times.alloc(n);
       CUDA_CHECK(cudaMemsetAsync(d_times.p, 0, n * sizeof(unsigned long long), st));
       b.warp_times = d_times.p;
-      launch_kubo_i<Draws, true>(h, b, grid, st);
+      launch_kubo_i<Draws, true>(h, b, grid, st, defer);
       std::vector<unsigned long long> host(n);
       d_times.download(host.data(), n, st);
       CUDA_CHECK(cudaStreamSynchronize(st));
@@ -480,9 +489,9 @@ void launch_kubo(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st) 
       }
       return;
     }
-    launch_kubo_i<Draws, true>(h, a, grid, st);
+    launch_kubo_i<Draws, true>(h, a, grid, st, defer);
   } else
-    launch_kubo_i<Draws, false>(h, a, grid, st);
+    launch_kubo_i<Draws, false>(h, a, grid, st, defer);
 }
 
 // nsteps x kubo_step on the device; sums -> dev_sums[nsteps][4]
@@ -519,8 +528,9 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   // group solver (counter-based streams only: a replayed stream has nothing to prepare in parallel)
   const bool   deep = h->opt_deep_thr > 0 && !h->replay;
   const double deep_thr = deep ? (double)h->opt_deep_thr : INFINITY;
-  h->d_defer_list.alloc((size_t)h->P);
-  h->d_defer_count.alloc(1);
+  h->d_hand_list[0].alloc((size_t)h->P);
+  h->d_hand_list[1].alloc((size_t)h->P);
+  h->d_hand_count.alloc(2);
   if (deep) {
     h->d_cur_dt.alloc((size_t)h->P); h->d_cur_ox.alloc((size_t)h->P); h->d_cur_oy.alloc((size_t)h->P); h->d_cur_oz.alloc((size_t)h->P);
     h->d_cur_step.alloc((size_t)h->P);
@@ -532,10 +542,12 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
       q.list[c] = h->d_list[read_buf][c].p;
       q.next_list[c] = h->d_list[1 - read_buf][c].p;
     }
-    q.list[kDeferred] = h->d_defer_list.p;
-    q.deferred_count_in = h->d_defer_count.p;
-    q.defer_list = h->d_defer_list.p;
-    q.defer_count = h->d_defer_count.p;
+    q.list[kDeferred] = h->d_hand_list[0].p;
+    q.list[kReturned] = h->d_hand_list[1].p;
+    q.hand_count = h->d_hand_count.p;
+    q.hand_list[0] = h->d_hand_list[0].p;
+    q.hand_list[1] = h->d_hand_list[1].p;
+    q.hand_to = h->d_hand_count.p;
     q.count = h->d_list_count[read_buf].p;
     q.next_count = h->d_list_count[1 - read_buf].p;
     q.head = h->d_list_head.p;
@@ -555,7 +567,7 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     const int n = (int)std::min(chunk, nsteps - done);
     CUDA_CHECK(cudaMemsetAsync(h->d_list_head.p, 0, kLists * sizeof(unsigned long long), st));
     CUDA_CHECK(cudaMemsetAsync(h->d_list_count[1 - h->cur_list].p, 0, kClasses * sizeof(uint32_t), st));
-    CUDA_CHECK(cudaMemsetAsync(h->d_defer_count.p, 0, sizeof(uint32_t), st));
+    CUDA_CHECK(cudaMemsetAsync(h->d_hand_count.p, 0, 2 * sizeof(uint32_t), st));
     KuboArgs a{};
     a.T = h->T;
     a.S = h->arrays();
@@ -564,15 +576,13 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     a.C.nevent = h->d_cur_nevent.p;
     a.draws = h->draws;
     a.q = lists(h->cur_list);
-    a.deep_on = deep ? 1 : 0;
+    a.round = 1;
+    a.yield_on = (deep && h->opt_deep_rounds > 1) ? 1 : 0;
     a.n_sites = h->sites.N;
     a.hot_blocks = (int32_t)((int64_t)grid * h->opt_hot_pct / 100);
     a.top_entries = (int32_t)h->opt_top_entries;
     a.deep_thr = deep_thr;
     a.deep_rate = a.deep_thr / dt;
-    a.park_min_s = (int32_t)h->opt_park_min_s;
-    a.park_min_e = (int32_t)h->opt_park_min_e;
-    a.park_age = (int32_t)h->opt_park_age;
     a.P = h->P;
     a.dt = dt;
     a.nsteps = n;
@@ -590,20 +600,41 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
       h->kernel_events.push_back(k1);
       CUDA_CHECK(cudaEventRecord(k0, st));
     }
-    if (h->replay)
-      launch_kubo<ReplayDraws>(h, a, grid, st);
-    else
-      launch_kubo<PhiloxDraws>(h, a, grid, st);
-    CUDA_CHECK(cudaGetLastError());
-    h->last_launches += 1;
-    if (deep) {  // the trap solver: class 4 and what the lanes deferred; blocks without work leave at once
-      const unsigned dgrid = (unsigned)((int64_t)h->sm_count * h->opt_deep_blocks);
-      if (h->trace_cap > 0 || h->opt_stats)
-        deep_kernel<true><<<dgrid, 128, 0, st>>>(a);
+    // Round 1: the lanes serve classes 0-3 and defer what lands in a deep trap; the trap solver serves class 4 and the
+    // deferred, and hands back what ends a time step outside a trap.  Round 2: the lanes finish the returned (deferring
+    // again), the trap solver finishes whatever is left and keeps it.  Kernels whose lists are empty leave at once.
+    const int rounds = deep ? (int)std::max<int64_t>(1, std::min<int64_t>(2, h->opt_deep_rounds)) : 1;
+    for (int round = 1; round <= rounds; ++round) {
+      a.round = round;
+      a.yield_on = (deep && round < rounds) ? 1 : 0;
+      if (round == 2) {  // the deferred list starts again (the trap solver has emptied it)
+        CUDA_CHECK(cudaMemsetAsync(h->d_hand_count.p, 0, sizeof(uint32_t), st));
+        CUDA_CHECK(cudaMemsetAsync(h->d_list_head.p + kDeferred, 0, sizeof(unsigned long long), st));
+      }
+      if (h->replay)
+        launch_kubo<ReplayDraws>(h, a, grid, st, false);
       else
-        deep_kernel<false><<<dgrid, 128, 0, st>>>(a);
+        launch_kubo<PhiloxDraws>(h, a, grid, st, deep);
       CUDA_CHECK(cudaGetLastError());
       h->last_launches += 1;
+      if (deep) {
+        cudaEvent_t d0 = nullptr, d1 = nullptr;
+        if (h->opt_time_kernels) {
+          CUDA_CHECK(cudaEventCreate(&d0));
+          CUDA_CHECK(cudaEventCreate(&d1));
+          h->deep_events.push_back(d0);
+          h->deep_events.push_back(d1);
+          CUDA_CHECK(cudaEventRecord(d0, st));
+        }
+        const unsigned dgrid = (unsigned)((int64_t)h->sm_count * h->opt_deep_blocks);
+        if (h->trace_cap > 0 || h->opt_stats)
+          deep_kernel<true><<<dgrid, 128, 0, st>>>(a);
+        else
+          deep_kernel<false><<<dgrid, 128, 0, st>>>(a);
+        CUDA_CHECK(cudaGetLastError());
+        if (d1) CUDA_CHECK(cudaEventRecord(d1, st));
+        h->last_launches += 1;
+      }
     }
     if (k1) CUDA_CHECK(cudaEventRecord(k1, st));
     h->cur_list = 1 - h->cur_list;
@@ -626,6 +657,14 @@ void finish_step_host(cntmc_t* h, int64_t nsteps, double* msd_out) {
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
+  h->deep_ms = 0;
+  for (size_t k = 0; k + 1 < h->deep_events.size(); k += 2) {
+    float dms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&dms, h->deep_events[k], h->deep_events[k + 1]));
+    h->deep_ms += dms;
+  }
+  for (cudaEvent_t ev : h->deep_events) cudaEventDestroy(ev);
+  h->deep_events.clear();
   h->kernel_ms = 0;
   h->kernel_launches = (int64_t)h->kernel_events.size() / 2;
   for (size_t k = 0; k + 1 < h->kernel_events.size(); k += 2) {
@@ -850,10 +889,13 @@ int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P,
     cudaStream_t st = h->stream;
     // the kernels index the site tables with what the caller hands in: refuse what would read out of bounds
     const int64_t N = h->sites.N;
+    unsigned bad_site = 0, bad_ff = 0;  // branch-free so that the compiler vectorises it (0.1 ms per 1e6 excitons)
     for (int64_t i = 0; i < P; ++i) {
-      if (site[i] < 0 || (int64_t)site[i] >= N) throw std::invalid_argument("host state: site index out of range");
-      if (!std::isfinite(ff[i])) throw std::invalid_argument("host state: free-flight time is not finite");
+      bad_site |= (unsigned)((uint32_t)site[i] >= (uint32_t)N);
+      bad_ff |= (unsigned)!(ff[i] - ff[i] == 0.0);
     }
+    if (bad_site) throw std::invalid_argument("host state: site index out of range");
+    if (bad_ff) throw std::invalid_argument("host state: free-flight time is not finite");
     if (P > h->capacity) h->alloc_excitons(P);
     if (P != h->P) h->trace_cap = 0;  // the trace buffers were sized for the previous population
     h->have_lists = false;  // the uploaded population has not been filed under activity classes yet
@@ -1299,15 +1341,12 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "deep_thr") {
       require(value >= 0 && value <= 1000000, "deep_thr must be in [0, 1e6] (0 = no group solver)");
       h->opt_deep_thr = value;
+    } else if (k == "deep_rounds") {
+      require(value >= 1 && value <= 2, "deep_rounds must be 1 or 2");
+      h->opt_deep_rounds = value;
     } else if (k == "deep_blocks") {
       require(value >= 1 && value <= 4, "deep_blocks must be 1 to 4 blocks per SM");
       h->opt_deep_blocks = value;
-    } else if (k == "park_min_s" || k == "park_min_e") {
-      require(value >= 1 && value <= 32, "park_min_* must be in [1, 32]");
-      (k == "park_min_s" ? h->opt_park_min_s : h->opt_park_min_e) = value;
-    } else if (k == "park_age") {
-      require(value >= 1 && value <= 1024, "park_age must be in [1, 1024]");
-      h->opt_park_age = value;
     } else if (k == "hot_pct") {
       require(value >= 0 && value <= 100, "hot_pct must be in [0, 100]");
       h->opt_hot_pct = value;
@@ -1341,9 +1380,7 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "hot_pct") return h->opt_hot_pct;
   if (k == "deep_thr") return h->opt_deep_thr;
   if (k == "deep_blocks") return h->opt_deep_blocks;
-  if (k == "park_min_s") return h->opt_park_min_s;
-  if (k == "park_min_e") return h->opt_park_min_e;
-  if (k == "park_age") return h->opt_park_age;
+  if (k == "deep_rounds") return h->opt_deep_rounds;
   if (k == "top_entries") return h->opt_top_entries;
   if (k == "runs") return h->opt_runs;
   if (k == "dirs") return h->opt_dirs;
@@ -1357,6 +1394,24 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
     if (k == "dbg_lane_busy") return (int64_t)ctrs[CTR_LANE_BUSY];
     if (k == "dbg_lane_idle") return (int64_t)ctrs[CTR_LANE_IDLE];
     if (k == "dbg_top_events") return (int64_t)ctrs[CTR_FAST];
+    if (k == "dbg_walk_events") return (int64_t)ctrs[CTR_WALK];
+    if (k == "dbg_deep_us") return (int64_t)(h->deep_ms * 1e3);
+    if (k == "dbg_returned") {
+      uint32_t v2[2] = {0, 0};
+      if (!h->d_hand_count.p || cudaMemcpy(v2, h->d_hand_count.p, sizeof v2, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+      return v2[1];
+    }
+    if (k == "dbg_deferred" || k == "dbg_class4") {  // sizes of the trap solver's two lists in the last launch
+      uint32_t v[kClasses] = {0};
+      if (k == "dbg_deferred") {  // of the last round
+        if (!h->d_hand_count.p || cudaMemcpy(v, h->d_hand_count.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return v[0];
+      }
+      if (!h->d_list_count[1 - h->cur_list].p ||
+          cudaMemcpy(v, h->d_list_count[1 - h->cur_list].p, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+      return v[4];
+    }
   }
   return -1;
 }

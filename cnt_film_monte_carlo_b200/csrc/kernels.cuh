@@ -80,6 +80,7 @@ __device__ __forceinline__ void init_draws<ReplayDraws>(ReplayDraws& D, const Dr
 enum { FLAG_STUCK = 0, FLAG_REPLAY = 1, FLAG_EMPTY_ROW = 2, FLAG_COUNT = 4 };
 enum {
   CTR_REINJECT = 0, CTR_GUARD = 1, CTR_CROSS = 2, CTR_PROBE = 3, CTR_QUEUE = 4, CTR_EVENTS = 5, CTR_FAST = 6,
+  CTR_WALK = 7,  // instrumented trap solver: events decided by the window walk
   // instrumented hop kernel only: warp residency (ns summed over warps), kernel span as seen from the device
   // (~first start and last exit, stored for atomicMax), number of warps, lane-iterations with / without an exciton
   CTR_WARP_NS = 8, CTR_T_FIRST_INV = 9, CTR_T_LAST = 10, CTR_WARPS = 11, CTR_LANE_BUSY = 12, CTR_LANE_IDLE = 13,
@@ -126,20 +127,20 @@ __global__ void __launch_bounds__(256) create_excitons_kernel(const CreateArgs a
 // active classes and "cold" blocks the quiet ones, so that warps mostly hold excitons that run the same branch of the
 // loop, and class 4 (the deep traps) goes to the blocks that run the group solver (see hop_loop).
 constexpr int kClasses = 5;
-constexpr int kLists = kClasses + 1;  // + the excitons deferred to the group solver during the launch
-constexpr int kDeferred = kClasses;
+constexpr int kLists = kClasses + 2;  // + the excitons handed over during the launch: lanes -> trap solver, and back
+constexpr int kDeferred = kClasses, kReturned = kClasses + 1;
 __device__ __forceinline__ int activity_class(double ev, double deep_thr) {
   return ev >= deep_thr ? 4 : ev >= 8.0 ? 3 : ev >= 1.0 ? 2 : ev >= 0.125 ? 1 : 0;
 }
 struct ClassLists {
-  const uint32_t*     list[kLists];           // excitons of each class, filed by the previous launch; [kDeferred]: this launch
+  const uint32_t*     list[kLists];           // excitons of each class, filed by the previous launch; [kDeferred], [kReturned]: this launch
   const uint32_t*     count;                  // [kClasses]
-  const uint32_t*     deferred_count_in;      // count of list[kDeferred] (second pass)
+  const uint32_t*     hand_count;             // [2] sizes of list[kDeferred], list[kReturned]
   unsigned long long* head;                   // [kLists] next unassigned position of each list
   uint32_t*           next_list[kClasses];    // being filled for the next launch
   uint32_t*           next_count;             // [kClasses]
-  uint32_t*           defer_list;             // being filled by the lane blocks of this launch
-  uint32_t*           defer_count;
+  uint32_t*           hand_list[2];           // being filled in this launch: [0] by kubo_kernel (deferred), [1] by deep_kernel (returned)
+  uint32_t*           hand_to;                // [2] their sizes
 };
 
 // file exciton e of the lanes flagged `mine` under their class `cls` (warp-aggregated append; call with the whole warp)
@@ -156,14 +157,15 @@ __device__ __forceinline__ void file_excitons(const ClassLists& q, bool mine, in
     }
   }
 }
-__device__ __forceinline__ void defer_excitons(const ClassLists& q, bool mine, uint32_t e, int lane, unsigned lt_mask) {
+// hand excitons over to the other kernel: which = 0 lanes -> trap solver (deferred), 1 trap solver -> lanes (returned)
+__device__ __forceinline__ void hand_over(const ClassLists& q, int which, bool mine, uint32_t e, int lane, unsigned lt_mask) {
   const unsigned m = __ballot_sync(0xffffffffu, mine);
   if (m) {
     uint32_t  base = 0;
     const int leader = __ffs(m) - 1;
-    if (lane == leader) base = atomicAdd(q.defer_count, (uint32_t)__popc(m));
+    if (lane == leader) base = atomicAdd(q.hand_to + which, (uint32_t)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (mine) q.defer_list[base + __popc(m & lt_mask)] = e;
+    if (mine) q.hand_list[which][base + __popc(m & lt_mask)] = e;
   }
 }
 // hand an exciton to every lane that `want`s one, from the n_serve lists named in `serve`, in that order (call with the
@@ -176,7 +178,7 @@ __device__ __forceinline__ bool take_exciton(const ClassLists& q, bool want, uin
   for (int k = 0; k < n_serve && need; ++k) {
     const int          c = (int)((serve >> (4 * k)) & 15u);
     const int          n = __popc(need), leader = __ffs(need) - 1;
-    const long long    cnt = (long long)(c == kDeferred ? *q.deferred_count_in : q.count[c]);
+    const long long    cnt = (long long)(c >= kClasses ? q.hand_count[c - kClasses] : q.count[c]);
     unsigned long long base = 0;
     if (lane == leader) base = (cnt > 0) ? atomicAdd(q.head + c, (unsigned long long)n) : (unsigned long long)cnt;
     base = __shfl_sync(0xffffffffu, base, leader);
@@ -215,13 +217,13 @@ struct KuboArgs {
   CursorArrays        C;
   DrawConfig          draws;
   ClassLists          q;
-  int32_t             deep_on;      // class 4 and the excitons that land in a deep trap are left to deep_kernel
+  int32_t             round;        // 1: the lists of the launch; 2: what the other kernel handed back during round 1
+  int32_t             yield_on;     // deep_kernel: an exciton that ends a time step outside a trap goes back to the lanes
   int32_t             hot_blocks;   // blocks [0, hot_blocks) serve the active classes first
   int64_t             n_sites;
   int32_t             top_entries;  // try the three widest entries of a row before searching it
   double              deep_thr;     // Gamma*dt from which an exciton belongs to the group solver (inf: never)
   double              deep_rate;    // the same as a rate: deep_thr / dt
-  int32_t             park_min_s, park_min_e, park_age;  // lane blocks: see hop_loop
   int64_t             P;
   double              dt;
   int32_t             nsteps;
@@ -304,9 +306,6 @@ struct LoopDraws<Draws, 1> {
 // excitons.  Nothing in the loop needs a barrier or a floating-point atomic: when a lane ends a step it writes its
 // squared displacement to the (step, exciton) record, and reduce_stage_kernel sums the records in a fixed order
 // afterwards, so the ensemble sums do not depend on which lane processed which exciton, nor on any tuning option.
-//   Parking: a warp pays the latency of the step-end path and of the event path whenever at least one lane needs
-//   each.  With park_min_s / park_min_e > 1 the path that fewer than that many lanes ask for is skipped (its lanes
-//   wait, at most park_age iterations) until enough lanes have gathered.
 //   Deferral: an exciton that lands in a deep trap (Gamma*dt >= deep_thr) would occupy its lane for thousands of
 //   sequential events while the other 31 idle at the end of the launch -- at 1e6 excitons that chain IS the launch
 //   time.  The lane stores it with its cursor (step, time left, events of the step, start-of-step position) and
@@ -328,7 +327,7 @@ struct LoopDraws<Draws, 1> {
 // Only the first lane of a group stores anything.
 //
 // kInstr adds what only tests and the roofline bookkeeping need (site traces, probe / crossing counters).
-template <typename Draws, bool kInstr, int G>
+template <typename Draws, bool kInstr, int G, bool kDefer>
 __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3][128], double (&s_old)[3][128]) {
   typedef typename LoopDraws<Draws, G>::type DrawsT;
   const int      tid = threadIdx.x, lane = threadIdx.x & 31;
@@ -337,7 +336,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
   const bool     hot_role = (int)blockIdx.x < a.hot_blocks;
-  const bool     deep_on = a.deep_on != 0;
+  constexpr bool deep_on = kDefer;  // compile-time: even switched off at run time, the hand-over code cost 2.5 % (profiles/round2_*)
   uint32_t       e = 0;
   Lane           L{};
   DrawsT         D{};
@@ -345,15 +344,14 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
   int32_t        step = 0;
   int32_t*       trace = nullptr;
   int32_t        trace_base = 0;  // events already in the exciton's trace when the current time step began
-  int32_t        waited = 0;      // iterations this lane's operation has been parked
   int            from = 0;        // the list the current exciton came from
+  uint32_t       n_walk = 0;      // (instrumented) events decided by the window walk
   unsigned long long t_enter = 0, it_busy = 0, it_idle = 0, t_dry = 0;
   int                iter = 0;
   if (kInstr) t_enter = global_ns();
 #if defined(CNTMC_PROFILE_SEGMENTS)
   L.seg_t = clock64();
 #endif
-  const bool park = (G == 1) && (a.park_min_s > 1 || a.park_min_e > 1);
   // trap solver: this lane's site of the window
   int32_t  win_b = -1;
   double   w_total = 0, w_inv = 0, w_lo0 = 0, w_hi0 = 0, w_lo1 = 0, w_hi1 = 0, w_lo2 = 0, w_hi2 = 0, w_qr = 0, w_ql = 0;
@@ -370,7 +368,6 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
     init_draws(D, a.draws, a.S, (int64_t)e);
     step = 0;
     dt_rem = a.dt;
-    waited = 0;
     s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
     s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;  // _old_pos = _pos (particle.cpp:59)
     if (G > 1 && from == kDeferred) {  // handed over in the middle of a time step
@@ -379,6 +376,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
       L.nevent = a.C.nevent[e];
       s_old[0][tid] = a.C.ox[e]; s_old[1][tid] = a.C.oy[e]; s_old[2][tid] = a.C.oz[e];
     }
+    if (G == 1 && from == kReturned) step = a.C.step[e];  // handed back at a step boundary
     if (kInstr && a.trace_sites) {  // the trace continues where the previous launch stopped
       trace_base = a.trace_counts[e];  // may exceed the capacity: events beyond it are counted, not recorded
       trace = (leader && trace_base < a.trace_cap) ? a.trace_sites + (int64_t)e * a.trace_cap + trace_base : nullptr;
@@ -391,8 +389,10 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
   const int      n_hot = deep_on ? 2 : 3, n_roles = (G > 1) ? 1 : 2;
   for (int role = 0; role < n_roles; ++role) {
     const bool     serve_hot = (role == 0) == hot_role;
-    const uint32_t serve = (G > 1) ? (4u | ((uint32_t)kDeferred << 4)) : serve_hot ? hot_lists : cold_lists;
-    const int      n_serve = (G > 1) ? 2 : serve_hot ? n_hot : 2;
+    // round 2 of a launch serves what the other kernel handed over during round 1
+    const uint32_t serve = (G > 1) ? (a.round == 2 ? (uint32_t)kDeferred : (4u | ((uint32_t)kDeferred << 4)))
+                                   : a.round == 2 ? (uint32_t)kReturned : serve_hot ? hot_lists : cold_lists;
+    const int      n_serve = (G > 1) ? (a.round == 2 ? 1 : 2) : a.round == 2 ? 1 : serve_hot ? n_hot : 2;
     int64_t        e64 = 0;
     bool           have = take_exciton(a.q, leader, serve, n_serve, lane, lt_mask, e64, from);
     if (G > 1) {
@@ -405,14 +405,16 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
       start();
     }
     while (__any_sync(kFullMask, have)) {
-      bool finished = false, did_event = false;
+      bool finished = false, did_event = false, did_step = false;
       if (kInstr) {
         if (have) ++it_busy; else ++it_idle;
         ++iter;
       }
+      bool walk_finished = false, walk_yield = false;
       if constexpr (G > 1) {
-        // ---- trap solver: up to G events from the window registers (see the comment above hop_loop)
-        const bool can = have && L.at_site && (L.ff <= dt_rem) && a.top_entries != 0 && a.n_sites >= G;
+        // ---- trap solver: up to G events, and the step ends between them, from the window registers
+        const bool can = have && !L.stuck && a.top_entries != 0 && a.T.dir != nullptr && a.n_sites >= G &&
+                         ((L.ff <= dt_rem) || L.at_site);
         if (can) {
           if (win_b < 0 || L.site < win_b || L.site >= win_b + G) {  // (re)centre the window: lane j takes site b + j
             int64_t b = (int64_t)L.site - (G / 2 - 1);
@@ -427,7 +429,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
             w_lo0 = t.lo0; w_hi0 = t.hi0; w_lo1 = t.lo1; w_hi1 = t.hi1; w_lo2 = t.lo2; w_hi2 = t.hi2;
             w_n0 = t.nbr0; w_n1 = t.nbr1; w_n2 = t.nbr2;
             // what particle::fly does with the heading on this site (particle.cpp:20-34): bit 0 = heading after a start
-            // to the right, bit 1 = after a start to the left, bit 2 = no chain neighbour at all (no motion)
+            // to the right, bit 1 = after a start to the left, bit 2 = link-less or odd chain (generic path)
             w_flags = ((w_right > -1) ? 1u : 0u) | ((w_left > -1) ? 0u : 2u) | ((w_left < 0 && w_right < 0) ? 4u : 0u) |
                       ((w_left == w_right) ? 4u : 0u);
           }
@@ -436,9 +438,8 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
             D.refill(L.ndraw);
             off = 0;
           }
-          const int k0 = (int)(off >> 1);
           // every lane: what would an event on MY site do with each of the prepared dice draws?
-          uint32_t tbl = 0;
+          uint32_t      tbl = 0;
           const int32_t my_site = win_b + (lane - gbase);
 #pragma unroll
           for (int k = 0; k < G; ++k) {
@@ -453,32 +454,87 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
             tbl |= (ok ? (uint32_t)di : 15u) << (4 * k);
           }
           const unsigned zero2 = __ballot_sync(gmask, D.r2 == 0u) >> gbase;  // a zero free-flight draw is redrawn (scatterer.h:76-78)
-          int      s_idx = L.site - win_b;
-          bool     heading = L.heading_right, moved = false;
-          double   ff = L.ff;
-          const uint32_t room = (kInstr && trace) ? (uint32_t)(a.trace_cap - trace_base) : 0u;
-          for (int k = k0; k < G; ++k) {
-            if (!(ff <= dt_rem)) break;  // the flight outlasts the step
+          int    s_idx = L.site - win_b, k = (int)(off >> 1);
+          bool   heading = L.heading_right, at = L.at_site, moved = false;
+          double ff = L.ff, px = L.px, py = L.py, pz = L.pz;  // the position counts only while `at` is false
+          for (int guard = 0; guard < 4 * G; ++guard) {
             const uint32_t fl = __shfl_sync(gmask, w_flags, gbase + s_idx);
             const double   qr = __shfl_sync(gmask, w_qr, gbase + s_idx), ql = __shfl_sync(gmask, w_ql, gbase + s_idx);
+            const bool     nh = heading ? (fl & 1u) != 0 : (fl & 2u) != 0;  // heading after the start of the flight
+            if (fl & 4u) break;  // link-less or odd chain: generic path
+            if (!(ff <= dt_rem)) {
+              // -- the flight outlasts the time step: particle::step's fly(dt) tail and monte_carlo::kubo_step's loop body
+              if (!at) break;                          // (a step end in mid-segment: generic path)
+              const double q = nh ? qr : ql;
+              if (q < dt_rem) break;                   // reaches the next site within the step: generic path
+              const int32_t  site = win_b + s_idx;
+              const SitePos  p0 = load_pos(a.T.pos + site);
+              const Quad     u = load_quad(reinterpret_cast<const char*>(a.T.dir + site) + (nh ? 0 : 32));
+              const double   kk = a.T.velocity * dt_rem;  // particle.cpp:48
+              const double   nx = p0.x + u.a * kk, ny = p0.y + u.b * kk, nz = p0.z + u.c * kk;
+              if (nx < a.T.rem_lo[0] || ny < a.T.rem_lo[1] || nz < a.T.rem_lo[2] || a.T.rem_hi[0] < nx || a.T.rem_hi[1] < ny ||
+                  a.T.rem_hi[2] < nz)
+                break;                                 // leaves the removal box: re-injection on the generic path
+              heading = nh;
+              ff -= dt_rem;                            // particle.cpp:79
+              const double dx = s_delta[0][tid] + (nx - s_old[0][tid]), dy = s_delta[1][tid] + (ny - s_old[1][tid]),
+                           dz = s_delta[2][tid] + (nz - s_old[2][tid]);  // particle.h:97
+              if (leader) {
+                double2* rec = reinterpret_cast<double2*>(a.stage + ((size_t)step * (size_t)a.P + (size_t)e));
+                __stcs(rec, make_double2(dx * dx, dy * dy));
+                __stcs(rec + 1, make_double2(dz * dz, (double)L.nevent));
+              }
+              s_delta[0][tid] = dx; s_delta[1][tid] = dy; s_delta[2][tid] = dz;
+              s_old[0][tid] = nx; s_old[1][tid] = ny; s_old[2][tid] = nz;
+              px = nx; py = ny; pz = nz;
+              at = false;
+              ++step;
+              dt_rem = a.dt;
+              if (kInstr) {
+                trace_base += (int32_t)L.nevent;
+                if (trace) trace = (trace_base < a.trace_cap) ? trace + L.nevent : nullptr;
+              }
+              L.nevent = 0;
+              moved = true;
+              if (step >= a.nsteps) {
+                walk_finished = true;
+                break;
+              }
+              if (a.yield_on && __shfl_sync(gmask, w_total, gbase + s_idx) < a.deep_rate) {  // not a trap: back to the lanes
+                walk_yield = true;
+                break;
+              }
+              continue;
+            }
+            // -- a scattering event with the k-th prepared pair of draws
+            if (k >= G) break;
+            double q;
+            if (at) {
+              q = nh ? qr : ql;
+            } else {  // the flight starts between two sites: particle.cpp:39-41 on the actual position
+              const int32_t next = __shfl_sync(gmask, nh ? w_right : w_left, gbase + s_idx);
+              const SitePos n = load_pos(a.T.pos + next);
+              q = div_by(norm3(px - n.x, py - n.y, pz - n.z), a.T.velocity, a.T.inv_velocity);
+            }
+            if (q < ff) break;  // the flight reaches the next site: generic path
             const uint32_t tb = __shfl_sync(gmask, tbl, gbase + s_idx);
-            const bool     still = (fl & 4u) != 0;  // link-less site: particle::fly returns at once (particle.cpp:11-12)
-            const bool     nh = heading ? (fl & 1u) != 0 : (fl & 2u) != 0;
-            const double   q = nh ? qr : ql;
-            if (still || q < ff) break;  // link-less or odd chains, and flights that reach the next site: generic path
             const uint32_t di = (tb >> (4 * k)) & 15u;
             if (di == 15u || ((zero2 >> k) & 1u)) break;
-            // event k: the flight stops on the way (its leg is never seen), the exciton hops to window site di
+            // the flight stops on the way (its leg is never seen), the exciton hops to window site di
             heading = nh;
             dt_rem -= ff;  // particle.cpp:63
             const double inv = __shfl_sync(gmask, w_inv, gbase + (int)di), lgk = __shfl_sync(gmask, D.lg, gbase + k);
             ff = -inv * lgk;  // scatterer.h:79
             s_idx = (int)di;
+            at = true;
+            const uint32_t room = (kInstr && trace) ? (uint32_t)(a.trace_cap - trace_base) : 0u;
             if (kInstr && trace != nullptr && L.nevent < room) trace[L.nevent] = win_b + s_idx;
             ++L.nevent;
             L.ndraw += 2u;
             L.nprobe += 2u;
             ++L.nfast;
+            if (kInstr) ++n_walk;
+            ++k;
             moved = true;
           }
           if (moved) {
@@ -489,28 +545,20 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
             L.right = __shfl_sync(gmask, w_right, gbase + s_idx);
             L.q_right = __shfl_sync(gmask, w_qr, gbase + s_idx);
             L.q_left = __shfl_sync(gmask, w_ql, gbase + s_idx);
-            L.at_site = true;
-            L.pos_valid = false;
+            L.at_site = at;
+            L.pos_valid = !at;
+            if (!at) {
+              L.px = px; L.py = py; L.pz = pz;
+            }
             L.hop_valid = false;
           }
         }
       }
       // One iteration = up to two operations per lane: first the end of a time step for the lanes whose free flight
       // outlasts the step, then a scattering event for the lanes whose flight ends inside the (possibly new) step.
-      const bool need_s = have && !(L.ff <= dt_rem);  // particle.cpp:62 false: the flight outlasts the step
-      bool       run_s = true, run_e = true;
-      if (park) {
-        const int  n_s = __popc(__ballot_sync(kFullMask, need_s)), n_e = __popc(__ballot_sync(kFullMask, have && !need_s));
-        const bool old = __any_sync(kFullMask, have && waited >= a.park_age);
-        run_s = n_s > 0 && (n_s >= a.park_min_s || n_e == 0 || old);
-        run_e = n_e > 0 && (n_e >= a.park_min_e || n_s == 0 || old);
-        if (!run_s && !run_e) {
-          run_s = n_s >= n_e;
-          run_e = !run_s;
-        }
-      }
+      const bool need_s = have && !walk_finished && !walk_yield && !(L.ff <= dt_rem);  // particle.cpp:62 false: the flight outlasts the step
       CNTMC_SEG(L, 6);  // loop head, refill
-      if (need_s && run_s) {
+      if (need_s) {
         const double t = dt_rem;
         const Leg    leg = fly(L, a.T, t, true);
         L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
@@ -530,26 +578,27 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
           if (trace) trace = (trace_base < a.trace_cap) ? trace + L.nevent : nullptr;
         }
         L.nevent = 0;
-        waited = 0;
+        did_step = true;
         finished = (step >= a.nsteps);
       }
       CNTMC_SEG(L, 5);  // step-end path (own, or waiting for the lanes that run it)
-      const bool need_e = have && !finished && (L.ff <= dt_rem);
-      if (need_e && run_e) {
+      const bool need_e = have && !finished && !walk_finished && !walk_yield && (L.ff <= dt_rem);
+      if (need_e) {
         const double t = L.ff;
         const Leg    leg = fly(L, a.T, t, false);
         dt_rem -= t;  // particle.cpp:63
         const uint32_t room = (kInstr && trace) ? (uint32_t)(a.trace_cap - trace_base) : 0u;
         after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, room, a.top_entries != 0);
         did_event = true;
-        waited = 0;
       }
-      if (park && have && !finished && ((need_s && !run_s) || (need_e && !run_e))) ++waited;
       CNTMC_SEG(L, 7);  // waiting for the other lanes of the warp to finish their events
-      finished = have && (finished || L.stuck);
-      // landed in a deep trap: the trap solver takes over
+      // trap solver: an exciton that ended a time step on a site that is no trap goes back to the lanes
+      bool yield = walk_yield;
+      if (G > 1 && a.yield_on && did_step && !did_event && !finished && !L.stuck && !(hop_info(L, a.T).total >= a.deep_rate)) yield = true;
+      finished = have && (finished || walk_finished || L.stuck);
+      // lanes: landed in a deep trap, the trap solver takes over
       const bool defer = (G == 1) && deep_on && did_event && !finished && L.hop_valid && L.hop.total >= a.deep_rate;
-      const bool release = finished || defer;
+      const bool release = finished || defer || yield;
       if (__any_sync(kFullMask, release)) {
         int cls = 0;
         if (release) {
@@ -557,20 +606,22 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
           L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
           if (leader) {
             store_lane(L, a.S, (int64_t)e);
+            if (yield) a.C.step[e] = step;  // at a step boundary: the step index is the whole cursor
             if (defer) {
               a.C.step[e] = step;
               a.C.dt_rem[e] = dt_rem;
               a.C.nevent[e] = L.nevent;
               a.C.ox[e] = s_old[0][tid]; a.C.oy[e] = s_old[1][tid]; a.C.oz[e] = s_old[2][tid];
             }
-            if (kInstr && a.trace_counts) a.trace_counts[e] = trace_base + (defer ? 0 : (int32_t)L.nevent);
+            if (kInstr && a.trace_counts) a.trace_counts[e] = trace_base + ((defer || yield) ? 0 : (int32_t)L.nevent);
             if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
             if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
           }
           if (finished) cls = activity_class(hop_info(L, a.T).total * a.dt, a.deep_thr);
         }
         file_excitons(a.q, finished && leader, cls, e, lane, lt_mask);
-        if (G == 1 && deep_on) defer_excitons(a.q, defer, e, lane, lt_mask);
+        if (G == 1 && deep_on) hand_over(a.q, 0, defer, e, lane, lt_mask);
+        if (G > 1 && a.yield_on) hand_over(a.q, 1, yield && leader, e, lane, lt_mask);
         bool got = take_exciton(a.q, release && leader, serve, n_serve, lane, lt_mask, e64, from);
         if (G > 1) {
           got = __shfl_sync(kFullMask, got ? 1 : 0, gbase) != 0;
@@ -597,6 +648,8 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
     const unsigned np = __reduce_add_sync(kFullMask, L.nprobe);
     const unsigned nf = __reduce_add_sync(kFullMask, L.nfast);
     if (lane == 0 && nf) atomicAdd(a.counters + CTR_FAST, (unsigned long long)nf);
+    const unsigned nw = __reduce_add_sync(kFullMask, leader ? n_walk : 0u);
+    if (lane == 0 && nw) atomicAdd(a.counters + CTR_WALK, (unsigned long long)nw);
     const unsigned long long t_exit = global_ns();
     atomicAdd(a.counters + CTR_LANE_BUSY, it_busy);
     atomicAdd(a.counters + CTR_LANE_IDLE, it_idle);
@@ -623,18 +676,19 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
 
 constexpr int kGroup = 8;  // lanes per exciton in the trap solver
 
-template <typename Draws, int kMinBlocks, bool kInstr>
+// kDefer: the lanes leave class 4 and whatever lands in a deep trap to deep_kernel (option deep_thr > 0)
+template <typename Draws, int kMinBlocks, bool kInstr, bool kDefer>
 __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a) {
   // The displacement accumulator and the position at the start of the step are only touched when a time step ends;
   // they live in shared memory (one slot per thread) so that the event path does not carry 12 registers of them.
   __shared__ double s_delta[3][128], s_old[3][128];
-  hop_loop<Draws, kInstr, 1>(a, s_delta, s_old);
+  hop_loop<Draws, kInstr, 1, kDefer>(a, s_delta, s_old);
 }
 // the trap solver: class 4 of the previous launch and the excitons kubo_kernel deferred in this one
 template <bool kInstr>
 __global__ void __launch_bounds__(128, 4) deep_kernel(const KuboArgs a) {
   __shared__ double s_delta[3][128], s_old[3][128];
-  hop_loop<PhiloxDraws, kInstr, kGroup>(a, s_delta, s_old);
+  hop_loop<PhiloxDraws, kInstr, kGroup, false>(a, s_delta, s_old);
 }
 
 

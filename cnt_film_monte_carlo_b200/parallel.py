@@ -55,7 +55,9 @@ class ShardedContacts:
 
     The contact rules are per exciton, so the populations the contacts are held at are split statically over the ranks
     (`c1_pop`, `c2_pop` = this rank's share, the first ranks hold the remainders) and every rank runs its own excitons
-    on a full copy of the film.  Streams must differ between ranks: `seed` mixes the rank into the run's seed.  Unlike
+    on a full copy of the film.  Streams must differ between ranks: `seed` mixes the rank into the run's seed, and
+    `configure(engine)` moves the rank's exciton ids to their own range (rank * 2^56 onwards), which alone guarantees that
+    no two ranks ever share a stream (the stream key is a bijection of the id's high half for a fixed seed).  Unlike
     the Green-Kubo flavour the trajectories depend on the number of ranks (birth order defines the exciton ids); the
     ensemble is the same.  The one exchange per engine call is the sum of the integer bins
     [nsteps][n_seg populations + (n_seg - 1) net crossings] (monte_carlo.h:566-573, 626-636)."""
@@ -65,6 +67,10 @@ class ShardedContacts:
         self.c1_pop = shard_range(c1_pop, rank, world)[1]
         self.c2_pop = shard_range(c2_pop, rank, world)[1]
         self.seed = (int(seed) + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
+
+    def configure(self, engine) -> None:
+        """Call before engine.init(): this rank's excitons are numbered from rank * 2^56."""
+        engine.set_option("gid_base_shift56", self.rank)
 
     def bins(self, local_bins):
         """Whole-ensemble bins from this rank's (numpy [nsteps][2*n_seg-1] int64, or a CUDA tensor filled by

@@ -164,10 +164,10 @@ int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites);
 /* ---- tuning (never changes results) ------------------------------------------------------------------------------------
  * chunk_steps  time steps per hop-kernel launch (default 64)          stage_mb     cap on the staging buffer in MiB (0 = auto)
  * hot_pct      share of the lane blocks that serve the most active excitons first (default 30)
- * deep_thr     Gamma*dt from which an exciton is handed to the trap solver (default 16; 0 = no trap solver)
- * deep_blocks  blocks per SM of the trap solver's launch (default 4)
- * park_min_s, park_min_e, park_age   lane blocks: the step-end / event path runs once that many lanes ask for it, or
- *              after a lane has waited park_age iterations (defaults 1, 1, 4 = no parking)
+ * deep_thr     Gamma*dt from which an exciton is handed to the trap solver, a second kernel that walks trapped excitons
+ *              from a register-resident window of site records (default 0 = off: bit-identical results, but slower on
+ *              every workload measured so far); deep_blocks (blocks per SM of its launch, default 4), deep_rounds
+ *              (2: it hands excitons that left their trap back to the lanes once per launch; default 2)
  * gid_base_shift56  contact mode: stream ids start at value * 2^56 (cntmc_multi keeps the GPUs' streams apart with it)
  * occupancy    resident 128-thread blocks per SM the hop kernel is compiled for (default 5)
  * top_entries  1: the three widest entries of a row are tried before the row is searched (default)

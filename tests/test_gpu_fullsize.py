@@ -35,7 +35,7 @@ def run(c2, opts, first=0, count=P, steps=(STEPS,), trace=0):
 
 
 def test_full_size_properties(c2):
-    e, p0, p1, msd = run(c2, dict(chunk_steps=64))
+    e, p0, p1, msd = run(c2, dict(chunk_steps=64, deep_thr=16))   # with the trap solver; the comparison run below without
     # every draw is accounted for: creation takes 3 (site, free flight, heading), an event 2, a re-injection 1
     assert int(p1["ndraw"].astype(np.int64).sum()) == 3 * P + 2 * e.hops() + e.reinjections()
     assert e.hops() > 20 * P * 0.5

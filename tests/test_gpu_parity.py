@@ -106,12 +106,12 @@ def test_chunking_scheduling_and_occupancy_do_not_change_results():
     mc = base_mc()
     states, msds = [], []
     # the first run is the plain loop (no group solver, no parking); every other scheduling must give the same bits
-    for opts in (dict(chunk_steps=64, occupancy=6, deep_thr=0), dict(chunk_steps=7, occupancy=4), dict(chunk_steps=1, deep_thr=8),
-                 dict(chunk_steps=200, occupancy=5, deep_thr=0), dict(chunk_steps=64, stage_mb=1, deep_blocks=1),
-                 dict(chunk_steps=8, hot_pct=0, park_min_s=8, park_min_e=4), dict(chunk_steps=3, hot_pct=100, park_min_e=8, park_age=2),
+    for opts in (dict(chunk_steps=64, occupancy=6, deep_thr=0), dict(chunk_steps=7, occupancy=4, deep_thr=16), dict(chunk_steps=1, deep_thr=8, deep_rounds=1),
+                 dict(chunk_steps=200, occupancy=5, deep_thr=0), dict(chunk_steps=64, stage_mb=1, deep_thr=16, deep_blocks=1),
+                 dict(chunk_steps=8, hot_pct=0, deep_thr=16), dict(chunk_steps=3, hot_pct=100, deep_thr=16, deep_blocks=1),
                  dict(chunk_steps=8, hot_pct=30, occupancy=6, deep_thr=1, deep_blocks=2),
-                 dict(top_entries=0), dict(top_entries=1, chunk_steps=16, deep_thr=0, park_min_s=4), dict(top_entries=0, runs=0, hot_pct=50),
-                 dict(dirs=0, chunk_steps=9, deep_thr=30), dict(runs=0, hot_pct=5, chunk_steps=33, park_min_s=32, park_min_e=32, park_age=1000)):
+                 dict(top_entries=0), dict(top_entries=1, chunk_steps=16, deep_thr=0), dict(top_entries=0, runs=0, hot_pct=50),
+                 dict(dirs=0, chunk_steps=9, deep_thr=30), dict(chunk_steps=40, deep_thr=2, deep_rounds=2), dict(chunk_steps=64, deep_thr=9, deep_rounds=1), dict(runs=0, hot_pct=5, chunk_steps=33, deep_thr=16)):
         e = Engine(mc)
         e.set_mesh(pos, ori)
         for k, v in opts.items():
@@ -135,8 +135,8 @@ def test_shortcuts_do_not_change_results_on_a_trimmed_film():
     pos, ori = film.film(NT=120, NP=80, a=5.0, LX=300.0, LY=60.0, seed=3)
     mc = base_mc(**{"trim limits": {"xlim": [2e-8, 2.6e-7], "ylim": [0.0, 5e-8], "zlim": [1e-8, 2.8e-7]}})
     res = []
-    for opts in (dict(top_entries=0, runs=0, dirs=0, deep_thr=0), dict(top_entries=1, runs=1, dirs=1), dict(top_entries=1, runs=1, dirs=0, deep_thr=0),
-                 dict(top_entries=0, runs=0, dirs=1, deep_thr=8, deep_blocks=3), dict(top_entries=1, runs=1, dirs=1, chunk_steps=5, park_min_s=6, park_min_e=3)):
+    for opts in (dict(top_entries=0, runs=0, dirs=0, deep_thr=0), dict(top_entries=1, runs=1, dirs=1, deep_thr=16), dict(top_entries=1, runs=1, dirs=0, deep_thr=0),
+                 dict(top_entries=0, runs=0, dirs=1, deep_thr=8, deep_blocks=3), dict(top_entries=1, runs=1, dirs=1, chunk_steps=5, deep_thr=12, deep_rounds=1)):
         e = Engine(mc)
         e.set_mesh(pos, ori)
         for k, v in opts.items():

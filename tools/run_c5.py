@@ -31,6 +31,7 @@ e = Engine(mc_block(1), device=local_rank, stream=stream.cuda_stream)
 e.set_mesh(pos, ori)
 if "CNTMC_C5_TOP" in os.environ:
     e.set_option("top_entries", int(os.environ["CNTMC_C5_TOP"]))   # 0: row search only
+sc.configure(e)
 t0 = time.time(); e.init(sc.c1_pop, sc.c2_pop, seed=sc.seed, capacity=int(7 * sc.c1_pop)); t_init = time.time() - t0
 n_seg = e.number_of_segments()
 bins = torch.zeros((per_call, 2 * n_seg - 1), dtype=torch.int64, device=dev)
