@@ -39,7 +39,7 @@ DT = 1e-13
 TRIM_WIDE = {"xlim": [-1e-5, 1e-5], "ylim": [-1e-5, 1e-5], "zlim": [-1e-5, 1e-5]}
 TRIM_INPUT_JSON = {"xlim": [-1e-6, 1e-6], "ylim": [0, 1e-7], "zlim": [-1e-6, 1e-6]}   # the reference's input.json:56-60
 WORKLOADS = {
-    "C1": dict(film="C1", mode="kubo", dt=1e-15, trim=TRIM_INPUT_JSON, excitons=2000, intervals=20000, chunk=256, scaling="weak",
+    "C1": dict(film="C1", mode="kubo", dt=1e-15, trim=TRIM_INPUT_JSON, excitons=2000, intervals=20000, chunk=4096, scaling="weak",
                text="C1: input.json verbatim (trim limits, dt 1e-15 s, 2000 excitons) on the 200-tube x 100-site stand-in film (seed 1234)"),
     "C2": dict(film="C2", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=1_000_000, intervals=100, chunk=64, scaling="weak",
                text="C2: 1000-tube x 100-site random CNT film (seed 1234), forster table 21x11x11x11, cutoff 20 nm"),

@@ -58,6 +58,7 @@ SIGNATURES = {
     "cntmc_get_inject": (C.c_int, [V, V]),
     "cntmc_csr_nnz": (C.c_int, [V, V]),
     "cntmc_get_csr": (C.c_int, [V, V, V, V]),
+    "cntmc_get_csr_row": (C.c_int, [V, I64, I64, V, V, V]),
     "cntmc_csr_midpoint_guards": (I64, [V]),
     "cntmc_csr_build_seconds": (D, [V]),
     "cntmc_get_particles": (C.c_int, [V, V, V, V, V, V, V]),

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <memory>
 #include <type_traits>
@@ -135,8 +136,11 @@ struct cntmc_handle {
   std::vector<int32_t> c1_sites, c2_sites;
   int64_t              c1_pop = 0, c2_pop = 0;
 
-  std::vector<uint64_t> row_ptr;  // [N+1]
-  std::vector<double>   max_rate, inv_max_rate;
+  // host mirrors of device tables, fetched when somebody asks (a 5e6-site film: 40 MB and 640 MB of downloads)
+  mutable std::vector<uint64_t> row_ptr;  // [N+1]
+  mutable std::vector<double>   max_rate, inv_max_rate;
+  uint64_t              nnz = 0;
+  DevBuf<uint64_t>      d_row_begin;  // [N+1]
   int64_t               midpoint_guards = 0;
   double                csr_seconds = 0;
 
@@ -205,12 +209,23 @@ struct cntmc_handle {
   double  kernel_ms = 0;
   int64_t kernel_launches = 0;
 
+  // cntmc_kubo_step_host_state: the host-resident population is stepped in slices, each on its own stream with its own
+  // exciton buffers and lists but the parent's tables, so that the copies of one slice overlap the kernels of the others
+  std::vector<std::unique_ptr<cntmc_handle>> slices;
+  bool    is_slice = false;
+  int64_t grid_share = 1;  // this handle's launches use 1/grid_share of the resident block slots
+  int64_t opt_host_slices = 4;
+  int64_t opt_slice_share = 0;  // a slice's launches take 1/this of the block slots (0: half the number of slices, so that the
+                                // blocks of a later slice move in as those of an earlier one run dry)
+
   double  time = 0;  // monte_carlo::_time (never initialised by the reference, monte_carlo.h:45; starts at 0 here)
   int64_t hops = 0, reinjections = 0, crossings = 0, probes = 0;
 
   ~cntmc_handle() {
+    slices.clear();
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (is_slice && stream) cudaStreamDestroy(stream);
   }
 
   ExcitonArrays arrays() { return ex.view(contact_mode); }
@@ -252,6 +267,28 @@ void cntmc_handle::reserve_contact(int64_t cap, int64_t keep) {
 }
 
 namespace {
+
+void use_device(const cntmc_t* h);
+// host mirrors of the row offsets / the rates, fetched on first use
+void need_row_ptr(const cntmc_t* h) {
+  if (!h->row_ptr.empty()) return;
+  use_device(h);
+  h->row_ptr.resize((size_t)h->sites.N + 1);
+  CUDA_CHECK(cudaMemcpy(h->row_ptr.data(), h->d_row_begin.p, h->row_ptr.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+}
+void need_rates(const cntmc_t* h) {
+  if (!h->max_rate.empty()) return;
+  use_device(h);
+  const size_t         N = (size_t)h->sites.N;
+  std::vector<SiteRec> rec(N);
+  CUDA_CHECK(cudaMemcpy(rec.data(), h->d_site.p, N * sizeof(SiteRec), cudaMemcpyDeviceToHost));
+  h->max_rate.resize(N);
+  h->inv_max_rate.resize(N);
+  for (size_t i = 0; i < N; ++i) {
+    h->max_rate[i] = rec[i].total;
+    h->inv_max_rate[i] = rec[i].inv_total;
+  }
+}
 
 void use_device(const cntmc_t* h) {
   if (h->device >= 0) CUDA_CHECK(cudaSetDevice(h->device));
@@ -320,30 +357,48 @@ void common_init(cntmc_t* h) {
   h->d_a2.upload(t.a2, st);
   h->d_rates.upload(t.rates, st);
 
-  // site geometry in site order and in bucket order
-  std::vector<SiteGeom> geom((size_t)N), cell_geom((size_t)N);
-  std::vector<PosRec>        posrec;
-  const std::vector<SiteRec> rec = make_site_records(h->sites, h->prm.velocity, posrec);
-  for (int64_t i = 0; i < N; ++i) {
-    SiteGeom& g = geom[(size_t)i];
-    g.px = h->sites.pos[0][(size_t)i]; g.py = h->sites.pos[1][(size_t)i]; g.pz = h->sites.pos[2][(size_t)i];
-    g.ox = h->sites.orient[0][(size_t)i]; g.oy = h->sites.orient[1][(size_t)i]; g.oz = h->sites.orient[2][(size_t)i];
-  }
-  for (int64_t q = 0; q < N; ++q) cell_geom[(size_t)q] = geom[(size_t)h->buckets.sites[(size_t)q]];
+  // site list (struct of arrays, 56 bytes per site) and the bucket order go up once; records, geometry copies and the row
+  // offsets are made on the device
+  DevBuf<double>   d_soa[6];
+  DevBuf<int32_t>  d_left, d_right, d_cell_sites;
   DevBuf<SiteGeom> d_geom, d_cell_geom;
-  DevBuf<int32_t>  d_cell_sites;
   DevBuf<int64_t>  d_cell_start;
   DevBuf<uint32_t> d_deg;
-  DevBuf<uint64_t> d_row_begin;
-  d_geom.upload(geom, st);
-  d_cell_geom.upload(cell_geom, st);
+  for (int c = 0; c < 3; ++c) {
+    d_soa[c].upload(h->sites.pos[c], st);
+    d_soa[3 + c].upload(h->sites.orient[c], st);
+  }
+  d_left.upload(h->sites.left, st);
+  d_right.upload(h->sites.right, st);
   d_cell_sites.upload(h->buckets.sites, st);
   d_cell_start.upload(h->buckets.start, st);
   d_deg.alloc((size_t)N);
-  h->d_site.upload(rec, st);
-  h->d_seg.upload(make_segment_times(rec), st);
-  h->d_dir.upload(make_direction_records(rec, posrec), st);
-  h->d_pos.upload(posrec, st);
+  d_geom.alloc((size_t)N);
+  d_cell_geom.alloc((size_t)N);
+  h->d_site.alloc((size_t)N);
+  h->d_pos.alloc((size_t)N);
+  h->d_dir.alloc((size_t)N);
+  h->d_seg.alloc((size_t)N + 2 * kSegPad);
+  CUDA_CHECK(cudaMemsetAsync(h->d_seg.p, 0xff, ((size_t)N + 2 * kSegPad) * sizeof(double), st));  // all-ones = a NaN: the padding
+  {
+    SiteSetupArgs sa{};
+    sa.px = d_soa[0].p; sa.py = d_soa[1].p; sa.pz = d_soa[2].p;
+    sa.ox = d_soa[3].p; sa.oy = d_soa[4].p; sa.oz = d_soa[5].p;
+    sa.left = d_left.p;
+    sa.right = d_right.p;
+    sa.N = N;
+    sa.velocity = h->prm.velocity;
+    sa.site = h->d_site.p;
+    sa.pos = h->d_pos.p;
+    sa.dir = h->d_dir.p;
+    sa.seg = h->d_seg.p + kSegPad;
+    sa.geom = d_geom.p;
+    sa.flags = h->d_flags.p;
+    site_records_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sa);
+    CUDA_CHECK(cudaGetLastError());
+    gather_geom_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_geom.p, d_cell_sites.p, N, d_cell_geom.p);
+    CUDA_CHECK(cudaGetLastError());
+  }
 
   CsrArgs a{};
   a.geom = d_geom.p;
@@ -359,6 +414,10 @@ void common_init(cntmc_t* h) {
   a.R.theta = h->d_theta.p; a.R.z = h->d_z.p; a.R.a1 = h->d_a1.p; a.R.a2 = h->d_a2.p; a.R.rates = h->d_rates.p;
   a.R.n_theta = (int32_t)t.theta.size(); a.R.n_z = (int32_t)t.z.size();
   a.R.n_a1 = (int32_t)t.a1.size(); a.R.n_a2 = (int32_t)t.a2.size();
+  grid_hint(t.theta.data(), a.R.n_theta, &a.R.start[0], &a.R.inv_step[0]);
+  grid_hint(t.z.data(), a.R.n_z, &a.R.start[1], &a.R.inv_step[1]);
+  grid_hint(t.a1.data(), a.R.n_a1, &a.R.start[2], &a.R.inv_step[2]);
+  grid_hint(t.a2.data(), a.R.n_a2, &a.R.start[3], &a.R.inv_step[3]);
   a.deg = d_deg.p;
   a.site = h->d_site.p;
   a.flags = h->d_flags.p;
@@ -369,16 +428,26 @@ void common_init(cntmc_t* h) {
   CUDA_CHECK(cudaEventRecord(h->ev0, st));
   csr_rows_kernel<false><<<grid, block, 0, st>>>(a);
   CUDA_CHECK(cudaGetLastError());
-  std::vector<uint32_t> deg((size_t)N);
-  d_deg.download(deg.data(), (size_t)N, st);
+  // row offsets: exclusive scan of the degrees on the device (stable in site index by construction); only nnz comes back
+  h->d_row_begin.alloc((size_t)N + 1);
+  widen_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, st>>>(d_deg.p, N, h->d_row_begin.p);
+  CUDA_CHECK(cudaGetLastError());
+  {
+    size_t bytes = 0;
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, h->d_row_begin.p, h->d_row_begin.p, (int)(N + 1), st));
+    h->sort_tmp.alloc(bytes);
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(h->sort_tmp.p, bytes, h->d_row_begin.p, h->d_row_begin.p, (int)(N + 1), st));
+  }
+  uint64_t nnz = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&nnz, h->d_row_begin.p + N, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
-  h->row_ptr.assign((size_t)N + 1, 0);
-  for (int64_t i = 0; i < N; ++i) h->row_ptr[(size_t)i + 1] = h->row_ptr[(size_t)i] + deg[(size_t)i];
-  const uint64_t nnz = h->row_ptr[(size_t)N];
   if (nnz >= (1ull << 32)) throw std::invalid_argument("neighbour table has >= 2^32 entries; not supported by this build");
-  d_row_begin.upload(h->row_ptr, st);
+  h->nnz = nnz;
+  h->row_ptr.clear();
+  h->max_rate.clear();
+  h->inv_max_rate.clear();
   h->d_row.alloc((size_t)nnz);
-  a.row_begin = d_row_begin.p;
+  a.row_begin = h->d_row_begin.p;
   a.row = h->d_row.p;
   csr_rows_kernel<true><<<grid, block, 0, st>>>(a);
   CUDA_CHECK(cudaGetLastError());
@@ -387,21 +456,14 @@ void common_init(cntmc_t* h) {
   unsigned long long ctrs[CTR_COUNT];
   h->d_flags.download(flags, FLAG_COUNT, st);
   h->d_counters.download(ctrs, CTR_COUNT, st);
-  std::vector<SiteRec> hop((size_t)N);
-  h->d_site.download(hop.data(), (size_t)N, st);
   CUDA_CHECK(cudaStreamSynchronize(st));
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->csr_seconds = ms * 1e-3;
   h->midpoint_guards = (int64_t)ctrs[CTR_GUARD];
+  if (flags[FLAG_BAD_LINKS]) throw std::invalid_argument("chain links of the site list are not symmetric");
   if (flags[FLAG_EMPTY_ROW])
     throw StateError("a site has no neighbour inside the hopping radius (undefined behaviour in the reference, scatterer.h:91)");
-  h->max_rate.resize((size_t)N);
-  h->inv_max_rate.resize((size_t)N);
-  for (int64_t i = 0; i < N; ++i) {
-    h->max_rate[(size_t)i] = hop[(size_t)i].total;
-    h->inv_max_rate[(size_t)i] = hop[(size_t)i].inv_total;
-  }
 
   h->T.site = h->d_site.p;
   h->T.seg = h->opt_runs ? h->d_seg.p + kSegPad : nullptr;
@@ -516,7 +578,8 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>({h->opt_chunk, by_budget, nsteps}));
   // persistent grid: as many 128-thread blocks as the SMs hold at the compiled occupancy, never more than needed
   const int64_t  want = (h->P + 127) / 128;
-  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)h->sm_count * h->opt_occupancy);
+  // (a slice of a host-resident population takes its share of the block slots: the slices' launches run side by side)
+  const unsigned grid = (unsigned)std::min<int64_t>(want, std::max<int64_t>(1, (int64_t)h->sm_count * h->opt_occupancy / h->grid_share));
   h->d_stage.alloc((size_t)chunk * (size_t)h->P);
   h->d_partial.alloc((size_t)chunk * kStageSplits * 4);
   // activity-class lists, double-buffered: [cur] is read by a launch, [1-cur] is filled by it
@@ -880,11 +943,34 @@ int cntmc_kubo_step_dev(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums)
   });
 }
 
+// a slice of the parent's simulation: same tables (borrowed pointers), own stream, exciton buffers, lists and staging
+static cntmc_handle* make_slice(cntmc_t* h) {
+  std::unique_ptr<cntmc_handle> s(new cntmc_handle);
+  s->is_slice = true;
+  s->prm = h->prm;
+  s->device = h->device;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreate(&s->ev0));
+  CUDA_CHECK(cudaEventCreate(&s->ev1));
+  s->sites.N = h->sites.N;
+  s->T = h->T;
+  s->initialised = true;
+  s->contact_mode = false;
+  s->sm_count = h->sm_count;
+  s->d_flags.alloc(FLAG_COUNT);
+  s->d_counters.alloc(CTR_COUNT);
+  CUDA_CHECK(cudaMemsetAsync(s->d_flags.p, 0, FLAG_COUNT * sizeof(int32_t), s->stream));
+  CUDA_CHECK(cudaMemsetAsync(s->d_counters.p, 0, CTR_COUNT * sizeof(unsigned long long), s->stream));
+  h->slices.emplace_back(std::move(s));
+  return h->slices.back().get();
+}
+
 int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P, int32_t* site, double* pos, double* delta,
                                double* ff, uint8_t* heading, uint32_t* ndraw, double* msd_out) {
   return guarded(h, [&] {
     require(h->initialised && !h->contact_mode, "call cntmc_kubo_init first");
     require(P > 0 && site && pos && delta && ff && heading && ndraw, "bad host-state arguments");
+    require(nsteps > 0, "nsteps must be positive");
     use_device(h);
     cudaStream_t st = h->stream;
     // the kernels index the site tables with what the caller hands in: refuse what would read out of bounds
@@ -896,11 +982,85 @@ int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P,
     }
     if (bad_site) throw std::invalid_argument("host state: site index out of range");
     if (bad_ff) throw std::invalid_argument("host state: free-flight time is not finite");
+    const size_t n = (size_t)P;
+    const int    K = (int)std::max<int64_t>(1, std::min<int64_t>(h->opt_host_slices, P / 65536));
+    if (K > 1 && h->trace_cap == 0 && !h->opt_stats && !h->opt_time_kernels) {
+      // ---- sliced: slice k = excitons [off_k, off_k + n_k) on its own stream; H2D of slice k+1 and D2H of slice k-1 overlap
+      // the kernels of slice k.  The streams are keyed by global id, so slicing changes no trajectory; the ensemble rows are
+      // the sum of the slices' rows (summation order differs from the unsliced call in the last bits only).
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      if (h->sm_count == 0) {
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
+      }
+      while ((int)h->slices.size() < K) make_slice(h);
+      std::vector<std::vector<double>> rows((size_t)K, std::vector<double>((size_t)nsteps * 4));
+      for (int k = 0; k < K; ++k) {
+        cntmc_handle* s = h->slices[(size_t)k].get();
+        const size_t  off = n * (size_t)k / (size_t)K, cnt = n * (size_t)(k + 1) / (size_t)K - off;
+        s->T = h->T;
+        s->opt_chunk = h->opt_chunk; s->opt_hot_pct = h->opt_hot_pct; s->opt_occupancy = h->opt_occupancy;
+        s->opt_top_entries = h->opt_top_entries; s->opt_deep_thr = h->opt_deep_thr; s->opt_deep_blocks = h->opt_deep_blocks;
+        s->opt_deep_rounds = h->opt_deep_rounds;
+        if (s->opt_stage_mb <= 0 && h->opt_stage_mb > 0) s->opt_stage_mb = std::max<int64_t>(64, h->opt_stage_mb / K);
+        s->grid_share = std::max<int64_t>(1, std::min<int64_t>(K, h->opt_slice_share > 0 ? h->opt_slice_share : (K + 1) / 2));
+        s->replay = h->replay;
+        s->draws = h->draws;
+        s->draws.first_gid = h->draws.first_gid + (uint64_t)off;
+        cudaStream_t ss = s->stream;
+        if ((int64_t)cnt > s->capacity) s->alloc_excitons((int64_t)cnt);
+        s->have_lists = false;
+        s->P = (int64_t)cnt;
+        s->ex.site.upload(site + off, cnt, ss);
+        s->ex.px.upload(pos + off, cnt, ss); s->ex.py.upload(pos + n + off, cnt, ss); s->ex.pz.upload(pos + 2 * n + off, cnt, ss);
+        s->ex.dx.upload(delta + off, cnt, ss); s->ex.dy.upload(delta + n + off, cnt, ss); s->ex.dz.upload(delta + 2 * n + off, cnt, ss);
+        s->ex.ff.upload(ff + off, cnt, ss);
+        s->ex.heading.upload(heading + off, cnt, ss);
+        s->ex.ndraw.upload(ndraw + off, cnt, ss);
+        s->d_sums.alloc((size_t)nsteps * 4);
+        kubo_step_device(s, dt, nsteps, s->d_sums.p);
+        s->ex.site.download(site + off, cnt, ss);
+        s->ex.px.download(pos + off, cnt, ss); s->ex.py.download(pos + n + off, cnt, ss); s->ex.pz.download(pos + 2 * n + off, cnt, ss);
+        s->ex.dx.download(delta + off, cnt, ss); s->ex.dy.download(delta + n + off, cnt, ss); s->ex.dz.download(delta + 2 * n + off, cnt, ss);
+        s->ex.ff.download(ff + off, cnt, ss);
+        s->ex.heading.download(heading + off, cnt, ss);
+        s->ex.ndraw.download(ndraw + off, cnt, ss);
+      }  // (nothing above may block the host: a copy to pageable memory would serialise the slices)
+      double ms = 0;
+      int64_t launches = 0;
+      for (int k = 0; k < K; ++k) {
+        cntmc_handle*      s = h->slices[(size_t)k].get();
+        unsigned long long ctrs[CTR_COUNT];
+        s->d_sums.download(rows[(size_t)k].data(), rows[(size_t)k].size(), s->stream);
+        s->d_counters.download(ctrs, CTR_COUNT, s->stream);
+        check_flags(s);  // synchronises the slice's stream
+        float sms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&sms, s->ev0, s->ev1));
+        ms = std::max<double>(ms, sms);
+        launches += s->last_launches;
+        h->reinjections += (int64_t)ctrs[CTR_REINJECT];
+        CUDA_CHECK(cudaMemsetAsync(s->d_counters.p, 0, CTR_COUNT * sizeof(unsigned long long), s->stream));
+      }
+      h->last_ms = ms;
+      h->last_launches = launches;
+      h->P = P;
+      h->have_lists = false;
+      for (int64_t q = 0; q < nsteps; ++q) {
+        h->time += dt;  // monte_carlo.cpp:341, one addition per step
+        double v[4] = {0, 0, 0, 0};
+        for (int k = 0; k < K; ++k)
+          for (int c = 0; c < 4; ++c) v[c] += rows[(size_t)k][(size_t)q * 4 + c];
+        h->hops += (int64_t)v[3];
+        if (msd_out)
+          for (int c = 0; c < 3; ++c) msd_out[q * 3 + c] = v[c] / double(P);  // monte_carlo.cpp:402-404
+      }
+      return;
+    }
     if (P > h->capacity) h->alloc_excitons(P);
     if (P != h->P) h->trace_cap = 0;  // the trace buffers were sized for the previous population
     h->have_lists = false;  // the uploaded population has not been filed under activity classes yet
     h->P = P;
-    const size_t n = (size_t)P;
     h->ex.site.upload(site, n, st);
     h->ex.px.upload(pos, n, st); h->ex.py.upload(pos + n, n, st); h->ex.pz.upload(pos + 2 * n, n, st);
     h->ex.dx.upload(delta, n, st); h->ex.dy.upload(delta + n, n, st); h->ex.dz.upload(delta + 2 * n, n, st);
@@ -1217,6 +1377,7 @@ int cntmc_get_sites(const cntmc_t* h, double* pos, double* orient, int32_t* left
     }
     if (left) std::copy(h->sites.left.begin(), h->sites.left.end(), left);
     if (right) std::copy(h->sites.right.begin(), h->sites.right.end(), right);
+    if (max_rate || inv_max_rate) need_rates(h);
     if (max_rate) std::copy(h->max_rate.begin(), h->max_rate.end(), max_rate);
     if (inv_max_rate) std::copy(h->inv_max_rate.begin(), h->inv_max_rate.end(), inv_max_rate);
   });
@@ -1256,16 +1417,18 @@ int cntmc_get_inject(const cntmc_t* h, int32_t* ids) {
 int cntmc_csr_nnz(const cntmc_t* h, int64_t* nnz) {
   return guarded(h, [&] {
     require(h->initialised, "not initialised");
-    *nnz = (int64_t)h->row_ptr.back();
+    *nnz = (int64_t)h->nnz;
   });
 }
 int cntmc_get_csr(const cntmc_t* h, int64_t* row_ptr, int32_t* nbr, double* cum) {
   return guarded(h, [&] {
     require(h->initialised, "not initialised");
     use_device(h);
-    const size_t nnz = (size_t)h->row_ptr.back();
-    if (row_ptr)
+    const size_t nnz = (size_t)h->nnz;
+    if (row_ptr) {
+      need_row_ptr(h);
       for (size_t i = 0; i < h->row_ptr.size(); ++i) row_ptr[i] = (int64_t)h->row_ptr[i];
+    }
     if (nbr || cum) {
       std::vector<RowEntry> rows(nnz);
       h->d_row.download(rows.data(), nnz, h->stream);
@@ -1273,6 +1436,27 @@ int cntmc_get_csr(const cntmc_t* h, int64_t* row_ptr, int32_t* nbr, double* cum)
       for (size_t k = 0; k < nnz; ++k) {
         if (nbr) nbr[k] = rows[k].nbr;
         if (cum) cum[k] = rows[k].cum;
+      }
+    }
+  });
+}
+int cntmc_get_csr_row(const cntmc_t* h, int64_t site, int64_t cap, int32_t* nbr, double* cum, int64_t* len) {
+  return guarded(h, [&] {
+    require(h->initialised, "not initialised");
+    require(site >= 0 && site < h->sites.N && len != nullptr, "bad row request");
+    use_device(h);
+    uint64_t be[2];  // the row's bounds straight from the device: no 40 MB mirror for a handful of rows
+    CUDA_CHECK(cudaMemcpy(be, h->d_row_begin.p + site, sizeof be, cudaMemcpyDeviceToHost));
+    const uint64_t b = be[0], d = be[1] - b;
+    *len = (int64_t)d;
+    const size_t n = (size_t)std::min<int64_t>((int64_t)d, cap);
+    if (n && (nbr || cum)) {
+      std::vector<RowEntry> row(n);
+      CUDA_CHECK(cudaMemcpyAsync(row.data(), h->d_row.p + b, n * sizeof(RowEntry), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      for (size_t k = 0; k < n; ++k) {
+        if (nbr) nbr[k] = row[k].nbr;
+        if (cum) cum[k] = row[k].cum;
       }
     }
   });
@@ -1333,7 +1517,7 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
   return guarded(h, [&] {
     const std::string k = name ? name : "";
     if (k == "chunk_steps") {
-      require(value >= 1 && value <= 256, "chunk_steps must be in [1, 256]");
+      require(value >= 1 && value <= 16384, "chunk_steps must be in [1, 16384]");
       h->opt_chunk = value;
     } else if (k == "gid_base_shift56") {
       require(value >= 0 && value < 128, "gid_base_shift56 must be in [0, 128)");
@@ -1341,6 +1525,12 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "deep_thr") {
       require(value >= 0 && value <= 1000000, "deep_thr must be in [0, 1e6] (0 = no group solver)");
       h->opt_deep_thr = value;
+    } else if (k == "slice_share") {
+      require(value >= 0 && value <= 16, "slice_share must be in [0, 16]");
+      h->opt_slice_share = value;
+    } else if (k == "host_slices") {
+      require(value >= 1 && value <= 16, "host_slices must be in [1, 16]");
+      h->opt_host_slices = value;
     } else if (k == "deep_rounds") {
       require(value >= 1 && value <= 2, "deep_rounds must be 1 or 2");
       h->opt_deep_rounds = value;
@@ -1381,6 +1571,7 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "deep_thr") return h->opt_deep_thr;
   if (k == "deep_blocks") return h->opt_deep_blocks;
   if (k == "deep_rounds") return h->opt_deep_rounds;
+  if (k == "host_slices") return h->opt_host_slices;
   if (k == "top_entries") return h->opt_top_entries;
   if (k == "runs") return h->opt_runs;
   if (k == "dirs") return h->opt_dirs;

@@ -15,7 +15,21 @@ struct RateTable {
   const double* a2;
   const double* rates;  // [theta][z][a1][a2], C order (scattering_struct.h:82-90)
   int32_t       n_theta, n_z, n_a1, n_a2;
+  // evenly spaced ascending grids (what linspace produces): where the nearest value must be, see argmin_abs_near.
+  // inv_step = 0 marks an axis that is searched in full (a loaded table with an irregular grid).
+  double        start[4], inv_step[4];
 };
+// axis k of a table: start and 1/step if the grid is ascending and evenly spaced to 1e-9 of its pitch, else {*, 0}
+inline void grid_hint(const double* g, int n, double* start, double* inv_step) {
+  *start = n > 0 ? g[0] : 0.0;
+  *inv_step = 0.0;
+  if (n < 2) return;
+  const double step = (g[n - 1] - g[0]) / double(n - 1);
+  if (!(step > 0)) return;
+  for (int i = 0; i < n; ++i)
+    if (!(fabs(g[i] - (g[0] + step * i)) <= 1e-9 * step)) return;
+  *inv_step = 1.0 / step;
+}
 
 // arma::abs(grid - x).index_min() (scattering_struct.h:42-49): first strict minimum from +inf, NaN never wins
 CNTMC_HD int argmin_abs(const double* grid, int n, double x) {
@@ -28,6 +42,32 @@ CNTMC_HD int argmin_abs(const double* grid, int n, double x) {
       idx = i;
     }
   }
+  return idx;
+}
+
+// The same index without scanning the whole grid.  |grid[i] - x| over an ascending grid falls, then rises, so the first
+// strict minimum lies within one place of round((x - start) / step) -- two places are scanned on either side, in ascending
+// order with the same strict comparison, starting from the same +inf / index 0, and a run of equal distances is followed
+// down to its first place, so ties, values far beyond the ends, NaN and infinities resolve exactly as in the full scan
+// (brute-force comparison: tests/test_host_core.py; whole tables against the oracle: test_oracle_*, test_gpu_*).
+CNTMC_HD int argmin_abs_near(const double* grid, int n, double x, double start, double inv_step) {
+  if (!(inv_step > 0)) return argmin_abs(grid, n, x);
+  const double f = (x - start) * inv_step;
+  int          j = (f > -4.0) ? ((f < (double)n + 4.0) ? (int)(f + 0.5) : n - 1) : 0;  // NaN, -inf -> 0
+  j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
+  const int lo = j - 2 < 0 ? 0 : j - 2, hi = j + 2 > n - 1 ? n - 1 : j + 2;
+  double    best = INFINITY;
+  int       idx = 0;
+  for (int i = lo; i <= hi; ++i) {
+    const double d = fabs(ro(grid + i) - x);
+    if (d < best) {
+      best = d;
+      idx = i;
+    }
+  }
+  // far beyond the upper end the rounded distances tie over many places (axis shifts of nearly parallel tubes reach 1e7
+  // grid pitches): the scan keeps the FIRST of them
+  while (idx > 0 && fabs(ro(grid + idx - 1) - x) == best) --idx;
   return idx;
 }
 
@@ -79,10 +119,10 @@ CNTMC_HD double pair_rate(const SiteGeom& s1, const SiteGeom& s2, const RateTabl
                     (s1.oy * axis_shift_1 + s1.py) - (s2.oy * axis_shift_2 + s2.py),
                     (s1.oz * axis_shift_1 + s1.pz) - (s2.oz * axis_shift_2 + s2.pz));
   }
-  const int i_th = argmin_abs(R.theta, R.n_theta, theta);
-  const int i_z = argmin_abs(R.z, R.n_z, z_shift);
-  const int i_1 = argmin_abs(R.a1, R.n_a1, axis_shift_1);
-  const int i_2 = argmin_abs(R.a2, R.n_a2, axis_shift_2);
+  const int i_th = argmin_abs_near(R.theta, R.n_theta, theta, R.start[0], R.inv_step[0]);
+  const int i_z = argmin_abs_near(R.z, R.n_z, z_shift, R.start[1], R.inv_step[1]);
+  const int i_1 = argmin_abs_near(R.a1, R.n_a1, axis_shift_1, R.start[2], R.inv_step[2]);
+  const int i_2 = argmin_abs_near(R.a2, R.n_a2, axis_shift_2, R.start[3], R.inv_step[3]);
   if (guard != nullptr && near_midpoint(R.theta, R.n_theta, i_th, theta, 1e-9)) *guard = true;
   return ro(R.rates + (((size_t)i_th * R.n_z + i_z) * R.n_a1 + i_1) * R.n_a2 + i_2);
 }

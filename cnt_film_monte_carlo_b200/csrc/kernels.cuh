@@ -77,7 +77,7 @@ __device__ __forceinline__ void init_draws<ReplayDraws>(ReplayDraws& D, const Dr
   D.init(dc.replay_draws, dc.replay_logs, dc.replay_off[g], dc.replay_off[g + 1]);
 }
 
-enum { FLAG_STUCK = 0, FLAG_REPLAY = 1, FLAG_EMPTY_ROW = 2, FLAG_COUNT = 4 };
+enum { FLAG_STUCK = 0, FLAG_REPLAY = 1, FLAG_EMPTY_ROW = 2, FLAG_BAD_LINKS = 3, FLAG_COUNT = 4 };
 enum {
   CTR_REINJECT = 0, CTR_GUARD = 1, CTR_CROSS = 2, CTR_PROBE = 3, CTR_QUEUE = 4, CTR_EVENTS = 5, CTR_FAST = 6,
   CTR_WALK = 7,  // instrumented trap solver: events decided by the window walk
@@ -960,6 +960,71 @@ __global__ void track_kernel(const TrackArgs a) {
   a.n_out[2] = (int64_t)L.nevent;
   if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
   if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
+}
+
+// ---- set-up on the device ---------------------------------------------------------------------------------------------------
+// Everything a site contributes to the tables except its row: chain links and the flight times to its two chain neighbours
+// (particle.cpp:39-41 for an exciton that sits on the site), its position record, the unit vectors towards the neighbours
+// (particle.cpp:47), the segment time shared with its memory neighbour (NaN if they are not each other's chain neighbours),
+// and its geometry for the table build.  One thread per site; IEEE sqrt and division, no contraction: the bits of the host
+// functions of the same name in host_setup.cpp (which the CPU tests run).
+struct SiteSetupArgs {
+  const double * px, *py, *pz, *ox, *oy, *oz;  // post-trim site list, struct of arrays
+  const int32_t *left, *right;
+  int64_t        N;
+  double         velocity;
+  SiteRec*       site;
+  PosRec*        pos;
+  DirRec*        dir;
+  double*        seg;   // [N], already offset by the padding
+  SiteGeom*      geom;  // [N] site order
+  int32_t*       flags;
+};
+__global__ void __launch_bounds__(256) site_records_kernel(const SiteSetupArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N) return;
+  const double  x = a.px[i], y = a.py[i], z = a.pz[i];
+  const int32_t l = a.left[i], r = a.right[i];
+  // create_scatterers + trim_scats always produce symmetric links (monte_carlo.h:249-262, 730-772)
+  if ((l > -1 && a.right[l] != (int32_t)i) || (r > -1 && a.left[r] != (int32_t)i) || (l > -1 && l == r)) atomicOr(a.flags + FLAG_BAD_LINKS, 1);
+  SiteRec rec{};
+  rec.left = l;
+  rec.right = r;
+  rec.q_left = rec.q_right = 0.0;
+  DirRec d{0, 0, 0, 0, 0, 0, 0, 0};
+  if (l > -1) {
+    rec.q_left = segment_time(x, y, z, a.px[l], a.py[l], a.pz[l], a.velocity);
+    const double wx = a.px[l] - x, wy = a.py[l] - y, wz = a.pz[l] - z, nn = norm3(wx, wy, wz), den = (nn > 0) ? nn : 1.0;
+    d.lx = wx / den; d.ly = wy / den; d.lz = wz / den;
+  }
+  if (r > -1) {
+    rec.q_right = segment_time(x, y, z, a.px[r], a.py[r], a.pz[r], a.velocity);
+    const double wx = a.px[r] - x, wy = a.py[r] - y, wz = a.pz[r] - z, nn = norm3(wx, wy, wz), den = (nn > 0) ? nn : 1.0;
+    d.rx = wx / den; d.ry = wy / den; d.rz = wz / den;
+  }
+  rec.top.nbr[0] = rec.top.nbr[1] = rec.top.nbr[2] = -1;  // rates, row and top entries: the table build
+  a.site[i] = rec;
+  a.pos[i] = PosRec{x, y, z, 0.0};
+  a.dir[i] = d;
+  a.geom[i] = SiteGeom{x, y, z, a.ox[i], a.oy[i], a.oz[i]};
+  // segment between sites i and i+1: usable by the run walk only if they are each other's chain neighbours and both sides
+  // computed the same time
+  double sg = __longlong_as_double(0x7ff8000000000000LL);
+  if (i + 1 < a.N && r == (int32_t)(i + 1) && a.left[i + 1] == (int32_t)i) {
+    const double back = segment_time(a.px[i + 1], a.py[i + 1], a.pz[i + 1], x, y, z, a.velocity);
+    if (__double_as_longlong(back) == __double_as_longlong(rec.q_right)) sg = rec.q_right;
+  }
+  a.seg[i] = sg;
+}
+// bucket-ordered copy of the geometry: candidates of one cell are contiguous for the table build
+__global__ void __launch_bounds__(256) gather_geom_kernel(const SiteGeom* geom, const int32_t* cell_sites, int64_t N, SiteGeom* cell_geom) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < N) cell_geom[q] = geom[cell_sites[q]];
+}
+__global__ void __launch_bounds__(256) widen_kernel(const uint32_t* deg, int64_t N, uint64_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = deg[i];
+  if (i == N) out[i] = 0;
 }
 
 // ---- K1: neighbour table ---------------------------------------------------------------------------------------------------

@@ -253,6 +253,18 @@ class Engine:
     def csr_midpoint_guards(self) -> int:
         return self.L.cntmc_csr_midpoint_guards(self.h)
 
+    def csr_nnz(self) -> int:
+        n = C.c_int64()
+        self._ck(self.L.cntmc_csr_nnz(self.h, C.byref(n)))
+        return n.value
+
+    def csr_row(self, site: int, cap: int = 8192):
+        """(nbr, cum) of one site's row (scatterer::find_neighbors of that site)"""
+        nbr, cum, n = np.empty(cap, np.int32), np.empty(cap), C.c_int64()
+        self._ck(self.L.cntmc_get_csr_row(self.h, site, cap, _p(nbr), _p(cum), C.byref(n)))
+        assert n.value <= cap
+        return nbr[:n.value].copy(), cum[:n.value].copy()
+
     def csr_build_seconds(self) -> float:
         return self.L.cntmc_csr_build_seconds(self.h)
 

@@ -147,6 +147,8 @@ int cntmc_get_inject(const cntmc_t* h, int32_t* ids);
 /* the neighbour table = scatterer::find_neighbors (scatterer.cpp:34-83) of every site, as CSR */
 int cntmc_csr_nnz(const cntmc_t* h, int64_t* nnz);
 int cntmc_get_csr(const cntmc_t* h, int64_t* row_ptr /* [N+1] */, int32_t* nbr /* [nnz] */, double* cum /* [nnz] */);
+/* one row of the table (tables of 1e9 entries are not read back whole): up to cap entries, *len = the row's length */
+int cntmc_get_csr_row(const cntmc_t* h, int64_t site, int64_t cap, int32_t* nbr, double* cum, int64_t* len);
 /* pairs whose theta fell within 1e-9 grid pitches of a grid midpoint (device acos vs glibc acos could disagree) */
 int64_t cntmc_csr_midpoint_guards(const cntmc_t* h);
 double  cntmc_csr_build_seconds(const cntmc_t* h);
@@ -168,6 +170,8 @@ int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites);
  *              from a register-resident window of site records (default 0 = off: bit-identical results, but slower on
  *              every workload measured so far); deep_blocks (blocks per SM of its launch, default 4), deep_rounds
  *              (2: it hands excitons that left their trap back to the lanes once per launch; default 2)
+ * host_slices  cntmc_kubo_step_host_state steps the uploaded population in this many slices on their own streams so that
+ *              the copies of one overlap the kernels of the others (default 4; populations below 65536 per slice: 1)
  * gid_base_shift56  contact mode: stream ids start at value * 2^56 (cntmc_multi keeps the GPUs' streams apart with it)
  * occupancy    resident 128-thread blocks per SM the hop kernel is compiled for (default 5)
  * top_entries  1: the three widest entries of a row are tried before the row is searched (default)

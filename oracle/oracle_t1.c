@@ -196,6 +196,7 @@ struct t1_sim {
   int32_t nb[3];
   int64_t *bucket_start;
   int32_t *bucket_sites;
+  int      lazy_rates; /* max_rate of a site is computed when first needed (full-size C4: 5e6 sites) */
   /* memoised rows */
   int      memo;
   int32_t** memo_ids;
@@ -488,8 +489,28 @@ void t1_set_memo(t1_sim* s, int on) {
 }
 
 /* scatterer.h:89-93 over all sites (monte_carlo.h:426-440); the reference is undefined for an empty row */
+void t1_set_lazy_rates(t1_sim* s, int on) { s->lazy_rates = on; }
+/* the rate fields of one site, exactly as the loop below computes them */
+static void ensure_rate(t1_sim* s, int64_t i) {
+  if (s->sites[i].inv_max_rate == s->sites[i].inv_max_rate) return; /* not NaN: known */
+  int32_t* ids = (int32_t*)malloc(ROW_CAP * sizeof(int32_t));
+  double*  cum = (double*)malloc(ROW_CAP * sizeof(double));
+  const int64_t d = find_neighbors(s, i, ids, cum, ROW_CAP);
+  if (d == 0 || d > ROW_CAP) {
+    fprintf(stderr, "[oracle/T1] a site has no neighbour (undefined behaviour in scatterer.h:91) or a row > %d\n", ROW_CAP);
+    abort();
+  }
+  s->sites[i].max_rate = cum[d - 1];
+  s->sites[i].inv_max_rate = 1. / s->sites[i].max_rate;
+  free(ids);
+  free(cum);
+}
 void t1_set_max_rate(t1_sim* s) {
   int bad = 0;
+  if (s->lazy_rates) {
+    for (int64_t i = 0; i < s->N; ++i) s->sites[i].max_rate = s->sites[i].inv_max_rate = NAN;
+    return;
+  }
 #pragma omp parallel
   {
     int32_t* ids = (int32_t*)malloc(ROW_CAP * sizeof(int32_t));
@@ -635,6 +656,7 @@ static double ff_time(t1_sim* s, exciton_t* e, int32_t site) {
   int32_t r;
   while ((r = draw(s, e)) == 0) {
   }
+  if (s->lazy_rates) ensure_rate(s, site);
   return -s->sites[site].inv_max_rate * log((double)r / (double)T1_RAND_MAX);
 }
 

@@ -42,6 +42,7 @@ void    t1_trim(t1_sim* s, const double xlim[2], const double ylim[2], const dou
 void    t1_find_domain(t1_sim* s);
 void    t1_build_buckets(t1_sim* s, double radius);
 void    t1_set_velocity(t1_sim* s, double v);
+void    t1_set_lazy_rates(t1_sim* s, int on); /* before t1_set_max_rate: compute a site's rate when first needed (same value) */
 void    t1_set_max_rate(t1_sim* s); /* one find_neighbors per site; aborts on an empty row like the reference's UB */
 void    t1_injection(t1_sim* s, int32_t n_sections);
 int64_t t1_num_sites(const t1_sim* s);

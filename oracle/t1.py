@@ -52,6 +52,7 @@ def _lib():
         "t1_build_buckets": (None, [V, D]),
         "t1_set_velocity": (None, [V, D]),
         "t1_set_max_rate": (None, [V]),
+        "t1_set_lazy_rates": (None, [V, C.c_int]),
         "t1_injection": (None, [V, I32]),
         "t1_num_sites": (I64, [V]),
         "t1_sites": (None, [V, V, V, V, V, V, V]),
@@ -203,6 +204,10 @@ class T1:
         self.setup_sites(mc, pos_nm, orient)
         self.n_seg = int(mc["number of segments"])
         self.L.t1_contacts_init(self.h, self.n_seg, c1_pop, c2_pop)
+
+    def set_lazy_rates(self, on: bool = True) -> None:
+        """Call before kubo_init: Gamma_i of a site is computed when first needed (the same value), for 5e6-site films."""
+        self.L.t1_set_lazy_rates(self.h, 1 if on else 0)
 
     def set_memo(self, on: bool = True) -> None:
         self.L.t1_set_memo(self.h, 1 if on else 0)

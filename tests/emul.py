@@ -157,3 +157,14 @@ class Emul:
     def select(self, cum, dice):
         cum = np.ascontiguousarray(cum, np.float64)
         return self.L.emul_select(_p(cum), len(cum), dice)
+
+
+def argmin_mismatches(grid, xs):
+    """(mismatches, hinted) of csr_core.h's windowed nearest-grid search against the reference's full scan"""
+    L = C.CDLL(build())
+    L.emul_argmin_mismatches.restype = C.c_int64
+    L.emul_argmin_mismatches.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    g, x = np.ascontiguousarray(grid, np.float64), np.ascontiguousarray(xs, np.float64)
+    hinted = C.c_int()
+    bad = L.emul_argmin_mismatches(_p(g), len(g), _p(x), len(x), C.byref(hinted))
+    return bad, bool(hinted.value)

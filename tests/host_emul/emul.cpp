@@ -83,6 +83,10 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
     }
     RateTable R{e->table.theta.data(), e->table.z.data(), e->table.a1.data(), e->table.a2.data(), e->table.rates.data(),
                 (int32_t)e->table.theta.size(), (int32_t)e->table.z.size(), (int32_t)e->table.a1.size(), (int32_t)e->table.a2.size()};
+    grid_hint(R.theta, R.n_theta, &R.start[0], &R.inv_step[0]);  // as cntmc_api.cu does: evenly spaced grids are not scanned in full
+    grid_hint(R.z, R.n_z, &R.start[1], &R.inv_step[1]);
+    grid_hint(R.a1, R.n_a1, &R.start[2], &R.inv_step[2]);
+    grid_hint(R.a2, R.n_a2, &R.start[3], &R.inv_step[3]);
     const double radius = e->prm.max_hopping_radius;
     e->row_ptr.assign((size_t)n + 1, 0);
     e->cum.clear();
@@ -359,4 +363,16 @@ extern "C" int64_t emul_op_sequences(Emul* e, double dt, int64_t nsteps, int64_t
     counts[i] = n;
   }
   return k;
+}
+
+// number of arguments for which the windowed nearest-grid search disagrees with the full scan (0 expected); *hinted = whether
+// the grid qualified for the windowed search at all
+extern "C" int64_t emul_argmin_mismatches(const double* grid, int n, const double* xs, int64_t m, int* hinted) {
+  double start = 0, inv_step = 0;
+  grid_hint(grid, n, &start, &inv_step);
+  *hinted = inv_step > 0 ? 1 : 0;
+  int64_t bad = 0;
+  for (int64_t k = 0; k < m; ++k)
+    if (argmin_abs(grid, n, xs[k]) != argmin_abs_near(grid, n, xs[k], start, inv_step)) ++bad;
+  return bad;
 }

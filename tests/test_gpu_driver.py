@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from cnt_film_monte_carlo_b200 import build, film
+from cnt_film_monte_carlo_b200.engine import Engine
 from cnt_film_monte_carlo_b200.monte_carlo import monte_carlo
 from oracle import t1 as T1m
 
@@ -94,3 +95,31 @@ def test_driver_reports_errors_like_the_reference(tmp_path):
     bad.write_text('{"cnts": {}}')
     r = subprocess.run([build.build_driver(), str(bad)], capture_output=True, text=True)
     assert r.returncode != 0 and 'does not contain "exciton monte carlo"' in r.stderr
+
+
+def test_cpp_driver_writes_individual_displacements(tmp_path, golden_small):
+    """monte_carlo::kubo_save_individual_particle_dispalcements (monte_carlo.cpp:345-380) in the C++ shim: three files, a
+    header line `time,+0,+1,...` (showpos), one row per call with the exciton's accumulated displacement -- and the same
+    text from the Python mirror of the class."""
+    g = golden_small
+    nsteps = 60
+    path, mc = write_case(tmp_path, g, "out_disp", **{"maximum time for kubo simulation [seconds]": g.dt * (nsteps - 0.5)})
+    r = subprocess.run([build.build_driver(), path, "--steps-per-call", "20", "--seed", "100", "--displacements", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    e = Engine(g.mc)
+    e.set_mesh(g.pos_nm, g.orient)
+    e.kubo_init()
+    e.kubo_create_particles(g.P, seed=100)
+    want = []
+    for _ in range(3):
+        e.kubo_step(g.dt, 20, want_msd=False)
+        want.append(e.particles()["delta"].copy())
+    for c, ax in enumerate("xyz"):
+        with open(os.path.join(mc["output directory"], "particle_dispalcement.%s.dat" % ax)) as f:
+            lines = f.read().splitlines()
+        assert lines[0] == "time" + "".join(",%+d" % i for i in range(g.P))
+        assert len(lines) == 4
+        for k in range(3):
+            vals = [float(v) for v in lines[1 + k].split(",")]
+            assert abs(vals[0] - g.dt * 20 * (k + 1)) < 1e-20 and lines[1 + k].startswith("+")
+            assert np.allclose(vals[1:], want[k][c], rtol=2e-6, atol=1e-30)

@@ -67,3 +67,30 @@ def test_full_size_properties(c2):
     pt = t.particles()
     assert np.array_equal(pt["site"], s1["site"][:n_o]) and np.array_equal(pt["heading"].astype(np.uint8), s1["heading"][:n_o])
     assert np.allclose(pt["pos"], s1["pos"][:, :n_o], rtol=1e-9, atol=1e-18) and np.allclose(pt["delta"], s1["delta"][:, :n_o], rtol=1e-9, atol=1e-18)
+
+
+def test_host_resident_population_in_slices(c2):
+    """cntmc_kubo_step_host_state steps a big uploaded population in slices on their own streams (copies overlap kernels):
+    per-exciton results are the bits of the resident run, the ensemble rows agree to the last bits' summation order."""
+    mc, pos, ori = c2
+    n = 400_000
+    runs = []
+    for slices in (1, 4, 3):
+        e = Engine(mc)
+        e.set_mesh(pos, ori)
+        e.set_option("host_slices", slices)
+        e.kubo_init()
+        e.kubo_create_particles(n, seed=5, first_global_id=1000)
+        state = e.particles()
+        msd = np.concatenate([e.kubo_step_host_state(DT, 40, state), e.kubo_step_host_state(DT, 25, state)])
+        runs.append((state, msd, e.hops(), e.reinjections(), e.time()))
+    res = Engine(mc)
+    res.set_mesh(pos, ori)
+    res.kubo_init()
+    res.kubo_create_particles(n, seed=5, first_global_id=1000)
+    msd_r = np.concatenate([res.kubo_step(DT, 40), res.kubo_step(DT, 25)])
+    pr = res.particles()
+    for state, msd, hops, reinj, t in runs:
+        assert all(np.array_equal(state[k], pr[k]) for k in pr)
+        assert np.allclose(msd, msd_r, rtol=1e-12, atol=0)
+        assert hops == res.hops() and reinj == res.reinjections() and t == res.time()

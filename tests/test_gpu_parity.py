@@ -257,3 +257,59 @@ def test_dense_film_long_rows_against_oracle():
     e.kubo_create_particles(3000, seed=2)
     e.kubo_step(1e-13, 12, want_msd=False)
     assert np.array_equal(e.particles()["site"], t.particles()["site"]) and e.hops() == t.hops()
+
+
+def test_host_state_refuses_what_would_read_out_of_bounds(golden_small):
+    """cntmc_kubo_step_host_state indexes the site tables with the caller's arrays: a bad site or a non-finite free-flight
+    time is an error, not a device fault; and the handle stays usable."""
+    g = golden_small
+    e = engine_for(g)
+    e.kubo_create_particles(64, seed=2)
+    state = e.particles()
+    bad = {k: v.copy() for k, v in state.items()}
+    bad["site"][5] = e.num_sites()
+    with pytest.raises(CntmcError, match="site index out of range"):
+        e.kubo_step_host_state(g.dt, 3, bad)
+    bad = {k: v.copy() for k, v in state.items()}
+    bad["ff"][7] = np.nan
+    with pytest.raises(CntmcError, match="not finite"):
+        e.kubo_step_host_state(g.dt, 3, bad)
+    e.kubo_step_host_state(g.dt, 3, state)
+
+
+def test_trace_capacity_is_a_clamp_not_a_buffer_size(golden_small):
+    """An exciton with more events than the trace holds is counted, not recorded: nothing is written past its slots,
+    neither within a launch nor when the next launch starts beyond the capacity."""
+    g = golden_small
+    full, tiny = engine_for(g), engine_for(g)
+    for e, cap in ((full, 1 << 12), (tiny, 4)):
+        e.kubo_create_particles(200, seed=13)
+        e.trace_enable(cap)
+        e.kubo_step(g.dt, 90, want_msd=False)
+        e.kubo_step(g.dt, 60, want_msd=False)
+    cf, sf = full.trace()
+    ct, st = tiny.trace()
+    assert np.array_equal(cf, ct) and cf.max() > 4          # counts run on beyond the capacity
+    assert np.array_equal(st, sf[:, :4])                    # the first `cap` events of every exciton, nothing else
+    pf, pt = full.particles(), tiny.particles()
+    assert all(np.array_equal(pf[k], pt[k]) for k in pf)
+
+
+def test_a_new_population_can_follow_a_failed_replay(golden_small):
+    """Device error flags are reported once: a replay list that runs out fails the call (CNTMC_ERR_REPLAY), and a fresh
+    population on the same handle runs without re-initialising it."""
+    g = golden_small
+    e = engine_for(g)
+    off, draws = g.z["draw_off"].astype(np.int64), g.z["draws"]
+    cut = off.copy()
+    cut[1:] = off[:-1] + np.minimum(np.diff(off), 4)      # at most four draws per exciton: creation passes, stepping runs dry
+    flat = np.concatenate([draws[off[i]:cut[i + 1]] for i in range(len(off) - 1)])
+    noff = np.zeros_like(off)
+    noff[1:] = np.cumsum(cut[1:] - off[:-1])
+    e.kubo_create_particles_replay(noff, flat, None)
+    with pytest.raises(CntmcError) as ei:
+        e.kubo_step(g.dt, int(g.nsteps))
+    assert ei.value.code == -4
+    e.kubo_create_particles(50, seed=3)
+    e.kubo_step(g.dt, 20)
+    assert e.hops() > 0

@@ -255,3 +255,40 @@ def test_untrimmed_bigger_film_against_oracle():
     pe, pt = e.particles(), t.particles()
     for k in STATE_KEYS:
         assert np.array_equal(pe[k], pt[k]), k
+
+
+def test_table_logarithm_is_within_one_ulp_of_glibc_on_every_possible_draw(tmp_path):
+    """fast_log_unit (csrc/fast_log.h) replaces the library logarithm in the free-flight draw: compared with glibc's log on
+    ALL 2^31 - 1 arguments r / RAND_MAX (same IEEE arithmetic on host and device, so the CPU run covers the kernel), and
+    div_by(r, RAND_MAX) with the division on all of them."""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "log_exh")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-fopenmp", "-x", "c++",
+                           os.path.join(root, "tools", "log_exhaustive.c"), "-o", exe])
+    out = json.loads(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+    assert out["args"] == 2147483647 and out["more"] == 0 and out["div_by_mismatch"] == 0
+    assert out["one_ulp"] < 0.002 * out["args"]      # 99.9 % of the results are glibc's bits, the rest one ulp away
+
+
+def test_windowed_grid_search_equals_the_reference_scan():
+    """scattering_struct::get_rate picks arma::abs(grid - x).index_min() (scattering_struct.h:42-49).  The table build
+    looks only near round((x - start)/step) on evenly spaced grids: same index for ties (exact midpoints: the first one
+    wins), grid values, values beyond the ends, NaN and infinities; irregular grids fall back to the full scan."""
+    import emul
+    rng = np.random.default_rng(0)
+    for lo, hi, n in ((0.0, 180 * 3.141592 / 180, 21), (1.5e-9, 10e-9, 11), (-10e-9, 10e-9, 11), (-8e-9, 8e-9, 9), (0.0, 1.0, 2), (5.0, 5.0, 1)):
+        grid = lo + (hi - lo) * np.arange(n) / max(1, n - 1) if n > 1 else np.array([lo])
+        step = (hi - lo) / max(1, n - 1)
+        mids = 0.5 * (grid[:-1] + grid[1:])
+        xs = np.concatenate([grid, mids, np.nextafter(mids, -np.inf), np.nextafter(mids, np.inf), np.nextafter(grid, np.inf),
+                             rng.uniform(lo - 3 * step - 1e-9, hi + 3 * step + 1e-9, 200000),
+                             [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e300, -1e300, lo - 1e-30, hi + 1e-30, 1.0, -1.0, 7.3e-2, 1e7 * step, -1e7 * step],
+                             hi + step * 10.0 ** rng.uniform(0, 17, 2000), lo - step * 10.0 ** rng.uniform(0, 17, 2000)])
+        bad, hinted = emul.argmin_mismatches(grid, xs)
+        assert bad == 0 and hinted == (n >= 2 and hi > lo)
+    irregular = np.array([0.0, 0.1, 0.5, 0.55, 2.0])
+    bad, hinted = emul.argmin_mismatches(irregular, rng.uniform(-1, 3, 10000))
+    assert bad == 0 and not hinted
