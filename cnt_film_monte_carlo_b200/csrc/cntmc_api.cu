@@ -141,7 +141,8 @@ struct cntmc_handle {
   mutable std::vector<double>   max_rate, inv_max_rate;
   uint64_t              nnz = 0;
   DevBuf<uint64_t>      d_row_begin;  // [N+1]
-  int64_t               midpoint_guards = 0;
+  int64_t               midpoint_guards = 0, midpoint_repairs = 0, midpoint_changed = 0;
+  int64_t               opt_guard_ppb = 1;  // theta within this many 1e-9 grid pitches of a midpoint flags its row
   double                csr_seconds = 0;
 
   // device tables
@@ -197,6 +198,7 @@ struct cntmc_handle {
   int64_t opt_deep_thr = 0;   // Gamma*dt from which an exciton belongs to the trap solver (0: no trap solver, the default:
                               // parity-green but slower on every workload measured, profiles/round2_trap_solver.txt)
   int64_t opt_deep_blocks = 4;  // blocks per SM of the trap solver's launch
+  int64_t opt_deep_group = 8;   // lanes per exciton in the trap solver (8: window walk; 1: the generic loop over trapped excitons only)
   int64_t opt_deep_rounds = 2;  // 2: the trap solver hands excitons that left their trap back to the lanes once per launch
   int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
   int64_t opt_stage_mb = 0;  // cap on the (step, exciton) staging buffer in MiB; shortens the launches if needed.
@@ -213,10 +215,11 @@ struct cntmc_handle {
   // exciton buffers and lists but the parent's tables, so that the copies of one slice overlap the kernels of the others
   std::vector<std::unique_ptr<cntmc_handle>> slices;
   bool    is_slice = false;
+  int64_t last_chunk = 0;  // time steps per launch the last step call actually used (option chunk_steps capped by the staging budget)
   int64_t grid_share = 1;  // this handle's launches use 1/grid_share of the resident block slots
   int64_t opt_host_slices = 4;
-  int64_t opt_slice_share = 0;  // a slice's launches take 1/this of the block slots (0: half the number of slices, so that the
-                                // blocks of a later slice move in as those of an earlier one run dry)
+  int64_t opt_slice_share = 0;  // a slice's launches take 1/this of the block slots (0: 1/number of slices, the best measured:
+                                // profiles/round2_e2e_slices.txt)
 
   double  time = 0;  // monte_carlo::_time (never initialised by the reference, monte_carlo.h:45; starts at 0 here)
   int64_t hops = 0, reinjections = 0, crossings = 0, probes = 0;
@@ -414,6 +417,12 @@ void common_init(cntmc_t* h) {
   a.R.theta = h->d_theta.p; a.R.z = h->d_z.p; a.R.a1 = h->d_a1.p; a.R.a2 = h->d_a2.p; a.R.rates = h->d_rates.p;
   a.R.n_theta = (int32_t)t.theta.size(); a.R.n_z = (int32_t)t.z.size();
   a.R.n_a1 = (int32_t)t.a1.size(); a.R.n_a2 = (int32_t)t.a2.size();
+  a.R.guard_tol = 1e-9 * (double)h->opt_guard_ppb;
+  DevBuf<int32_t> d_guard_sites;
+  const int32_t   guard_cap = 1 << 20;
+  d_guard_sites.alloc((size_t)guard_cap);
+  a.guard_sites = d_guard_sites.p;
+  a.guard_cap = guard_cap;
   grid_hint(t.theta.data(), a.R.n_theta, &a.R.start[0], &a.R.inv_step[0]);
   grid_hint(t.z.data(), a.R.n_z, &a.R.start[1], &a.R.inv_step[1]);
   grid_hint(t.a1.data(), a.R.n_a1, &a.R.start[2], &a.R.inv_step[2]);
@@ -461,6 +470,68 @@ void common_init(cntmc_t* h) {
   CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->csr_seconds = ms * 1e-3;
   h->midpoint_guards = (int64_t)ctrs[CTR_GUARD];
+  h->midpoint_repairs = h->midpoint_changed = 0;
+  if (h->midpoint_guards > 0) {  // expected: none.  The flagged rows again, on the host, with glibc's acos; patched in place.
+    if (h->midpoint_guards > guard_cap) throw StateError("too many rows with a theta next to a grid midpoint to repair");
+    std::vector<int32_t> gs((size_t)h->midpoint_guards);
+    d_guard_sites.download(gs.data(), gs.size(), st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    std::sort(gs.begin(), gs.end());
+    RateTable RH = a.R;  // the same table through host pointers
+    RH.theta = t.theta.data(); RH.z = t.z.data(); RH.a1 = t.a1.data(); RH.a2 = t.a2.data(); RH.rates = t.rates.data();
+    auto geom_of = [&](int64_t k) {
+      return SiteGeom{h->sites.pos[0][(size_t)k], h->sites.pos[1][(size_t)k], h->sites.pos[2][(size_t)k],
+                      h->sites.orient[0][(size_t)k], h->sites.orient[1][(size_t)k], h->sites.orient[2][(size_t)k]};
+    };
+    std::vector<RowEntry> row, old;
+    for (int32_t i : gs) {
+      const SiteGeom s1 = geom_of(i);
+      const int      cx = cell_coord(s1.px, a.lo[0], R), cy = cell_coord(s1.py, a.lo[1], R), cz = cell_coord(s1.pz, a.lo[2], R);
+      row.clear();
+      TopEntries top;
+      top.clear();
+      double acc = 0.0;
+      for (int c = 0; c < 27; ++c) {  // the kernel's enumeration: monte_carlo.h:402-411, cells in list order
+        const int ix = cx - 1 + c / 9, iy = cy - 1 + (c / 3) % 3, iz = cz - 1 + c % 3;
+        if (!(ix > -1 && ix < a.nb[0] && iy > -1 && iy < a.nb[1] && iz > -1 && iz < a.nb[2])) continue;
+        const int64_t b = (int64_t)ix + (int64_t)iy * a.nb[0] + (int64_t)iz * a.nb[0] * a.nb[1];
+        for (int64_t q = h->buckets.start[(size_t)b]; q < h->buckets.start[(size_t)b + 1]; ++q) {
+          const int32_t  j = h->buckets.sites[(size_t)q];
+          const SiteGeom s2 = geom_of(j);
+          if (!within_cutoff(s1, s2, R)) continue;
+          const double rate = pair_rate(s1, s2, RH, nullptr);  // host build: acos is glibc's
+          const double below = row.empty() ? -1.0 : acc;
+          acc = row.empty() ? rate : acc + rate;
+          top.add(rate, below, acc, j);
+          row.push_back(RowEntry{acc, j, 0});
+        }
+      }
+      uint64_t be[2];
+      CUDA_CHECK(cudaMemcpyAsync(be, h->d_row_begin.p + i, sizeof be, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      if (be[1] - be[0] != row.size()) throw StateError("host and device disagree on the length of a row");
+      old.resize(row.size());
+      CUDA_CHECK(cudaMemcpyAsync(old.data(), h->d_row.p + be[0], row.size() * sizeof(RowEntry), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      ++h->midpoint_repairs;
+      if (memcmp(old.data(), row.data(), row.size() * sizeof(RowEntry)) == 0) continue;  // glibc agrees: nothing to patch
+      ++h->midpoint_changed;
+      SiteRec rec;
+      CUDA_CHECK(cudaMemcpyAsync(&rec, h->d_site.p + i, sizeof rec, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      rec.total = acc;
+      rec.inv_total = row.empty() ? 0.0 : 1. / acc;
+      struct CumView {
+        const RowEntry* r;
+        double          operator[](uint32_t k) const { return r[k].cum; }
+      };
+      build_guide(CumView{row.data()}, (uint32_t)row.size(), acc, rec.guide);
+      top.store(rec.top);
+      CUDA_CHECK(cudaMemcpyAsync(h->d_row.p + be[0], row.data(), row.size() * sizeof(RowEntry), cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaMemcpyAsync(h->d_site.p + i, &rec, sizeof rec, cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+  }
   if (flags[FLAG_BAD_LINKS]) throw std::invalid_argument("chain links of the site list are not symmetric");
   if (flags[FLAG_EMPTY_ROW])
     throw StateError("a site has no neighbour inside the hopping radius (undefined behaviour in the reference, scatterer.h:91)");
@@ -580,6 +651,7 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   const int64_t  want = (h->P + 127) / 128;
   // (a slice of a host-resident population takes its share of the block slots: the slices' launches run side by side)
   const unsigned grid = (unsigned)std::min<int64_t>(want, std::max<int64_t>(1, (int64_t)h->sm_count * h->opt_occupancy / h->grid_share));
+  h->last_chunk = chunk;
   h->d_stage.alloc((size_t)chunk * (size_t)h->P);
   h->d_partial.alloc((size_t)chunk * kStageSplits * 4);
   // activity-class lists, double-buffered: [cur] is read by a launch, [1-cur] is filled by it
@@ -690,7 +762,14 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
           CUDA_CHECK(cudaEventRecord(d0, st));
         }
         const unsigned dgrid = (unsigned)((int64_t)h->sm_count * h->opt_deep_blocks);
-        if (h->trace_cap > 0 || h->opt_stats)
+        const bool instr = h->trace_cap > 0 || h->opt_stats;
+        if (h->opt_deep_group == 1) {
+          const unsigned lgrid = (unsigned)((int64_t)h->sm_count * 5);
+          if (instr)
+            trap_lanes_kernel<true><<<lgrid, 128, 0, st>>>(a);
+          else
+            trap_lanes_kernel<false><<<lgrid, 128, 0, st>>>(a);
+        } else if (instr)
           deep_kernel<true><<<dgrid, 128, 0, st>>>(a);
         else
           deep_kernel<false><<<dgrid, 128, 0, st>>>(a);
@@ -1004,7 +1083,7 @@ int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P,
         s->opt_top_entries = h->opt_top_entries; s->opt_deep_thr = h->opt_deep_thr; s->opt_deep_blocks = h->opt_deep_blocks;
         s->opt_deep_rounds = h->opt_deep_rounds;
         if (s->opt_stage_mb <= 0 && h->opt_stage_mb > 0) s->opt_stage_mb = std::max<int64_t>(64, h->opt_stage_mb / K);
-        s->grid_share = std::max<int64_t>(1, std::min<int64_t>(K, h->opt_slice_share > 0 ? h->opt_slice_share : (K + 1) / 2));
+        s->grid_share = std::max<int64_t>(1, std::min<int64_t>(K, h->opt_slice_share > 0 ? h->opt_slice_share : K));
         s->replay = h->replay;
         s->draws = h->draws;
         s->draws.first_gid = h->draws.first_gid + (uint64_t)off;
@@ -1528,9 +1607,16 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "slice_share") {
       require(value >= 0 && value <= 16, "slice_share must be in [0, 16]");
       h->opt_slice_share = value;
+    } else if (k == "guard_ppb") {
+      require(value >= 1 && value <= 1000000000, "guard_ppb must be in [1, 1e9]");
+      require(!h->initialised, "guard_ppb must precede initialisation");
+      h->opt_guard_ppb = value;
     } else if (k == "host_slices") {
       require(value >= 1 && value <= 16, "host_slices must be in [1, 16]");
       h->opt_host_slices = value;
+    } else if (k == "deep_group") {
+      require(value == 1 || value == 8, "deep_group must be 1 or 8");
+      h->opt_deep_group = value;
     } else if (k == "deep_rounds") {
       require(value >= 1 && value <= 2, "deep_rounds must be 1 or 2");
       h->opt_deep_rounds = value;
@@ -1571,7 +1657,12 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "deep_thr") return h->opt_deep_thr;
   if (k == "deep_blocks") return h->opt_deep_blocks;
   if (k == "deep_rounds") return h->opt_deep_rounds;
+  if (k == "deep_group") return h->opt_deep_group;
   if (k == "host_slices") return h->opt_host_slices;
+  if (k == "guard_ppb") return h->opt_guard_ppb;
+  if (k == "dbg_last_chunk") return h->last_chunk;
+  if (k == "dbg_midpoint_repairs") return h->midpoint_repairs;
+  if (k == "dbg_midpoint_changed") return h->midpoint_changed;
   if (k == "top_entries") return h->opt_top_entries;
   if (k == "runs") return h->opt_runs;
   if (k == "dirs") return h->opt_dirs;

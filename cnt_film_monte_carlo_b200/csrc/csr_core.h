@@ -18,6 +18,7 @@ struct RateTable {
   // evenly spaced ascending grids (what linspace produces): where the nearest value must be, see argmin_abs_near.
   // inv_step = 0 marks an axis that is searched in full (a loaded table with an irregular grid).
   double        start[4], inv_step[4];
+  double        guard_tol;  // a theta within this many grid pitches of a midpoint flags its row (see pair_rate)
 };
 // axis k of a table: start and 1/step if the grid is ascending and evenly spaced to 1e-9 of its pitch, else {*, 0}
 inline void grid_hint(const double* g, int n, double* start, double* inv_step) {
@@ -96,8 +97,10 @@ CNTMC_HD bool within_cutoff(const SiteGeom& s1, const SiteGeom& s2, double radiu
   return (distance < radius) && (distance > kMinDist);
 }
 
-// scatterer.cpp:44-63 for an accepted pair; s1 is the departure site.  *guard is set when theta is within 1e-9 pitch
-// of a grid midpoint (the only place where the device's acos could change an index relative to glibc).
+// scatterer.cpp:44-63 for an accepted pair; s1 is the departure site.  *guard is set when theta is within R.guard_tol
+// (1e-9) pitches of a grid midpoint -- the only place where the device's acos, which may differ from glibc's in the last
+// place, could pick another index than the reference.  Rows flagged this way are recomputed on the host with glibc's acos
+// and patched in (cntmc_api.cu, repair_flagged_rows).
 CNTMC_HD double pair_rate(const SiteGeom& s1, const SiteGeom& s2, const RateTable& R, bool* guard) {
   const double dRx = s1.px - s2.px, dRy = s1.py - s2.py, dRz = s1.pz - s2.pz;
   const double cosTheta = dot3(s1.ox, s1.oy, s1.oz, s2.ox, s2.oy, s2.oz);
@@ -123,7 +126,7 @@ CNTMC_HD double pair_rate(const SiteGeom& s1, const SiteGeom& s2, const RateTabl
   const int i_z = argmin_abs_near(R.z, R.n_z, z_shift, R.start[1], R.inv_step[1]);
   const int i_1 = argmin_abs_near(R.a1, R.n_a1, axis_shift_1, R.start[2], R.inv_step[2]);
   const int i_2 = argmin_abs_near(R.a2, R.n_a2, axis_shift_2, R.start[3], R.inv_step[3]);
-  if (guard != nullptr && near_midpoint(R.theta, R.n_theta, i_th, theta, 1e-9)) *guard = true;
+  if (guard != nullptr && near_midpoint(R.theta, R.n_theta, i_th, theta, R.guard_tol)) *guard = true;
   return ro(R.rates + (((size_t)i_th * R.n_z + i_z) * R.n_a1 + i_1) * R.n_a2 + i_2);
 }
 

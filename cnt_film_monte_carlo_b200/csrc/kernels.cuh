@@ -327,7 +327,7 @@ struct LoopDraws<Draws, 1> {
 // Only the first lane of a group stores anything.
 //
 // kInstr adds what only tests and the roofline bookkeeping need (site traces, probe / crossing counters).
-template <typename Draws, bool kInstr, int G, bool kDefer>
+template <typename Draws, bool kInstr, int G, bool kDefer, bool kTrap>
 __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3][128], double (&s_old)[3][128]) {
   typedef typename LoopDraws<Draws, G>::type DrawsT;
   const int      tid = threadIdx.x, lane = threadIdx.x & 31;
@@ -370,13 +370,13 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
     dt_rem = a.dt;
     s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
     s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;  // _old_pos = _pos (particle.cpp:59)
-    if (G > 1 && from == kDeferred) {  // handed over in the middle of a time step
+    if (kTrap && from == kDeferred) {  // handed over in the middle of a time step
       step = a.C.step[e];
       dt_rem = a.C.dt_rem[e];
       L.nevent = a.C.nevent[e];
       s_old[0][tid] = a.C.ox[e]; s_old[1][tid] = a.C.oy[e]; s_old[2][tid] = a.C.oz[e];
     }
-    if (G == 1 && from == kReturned) step = a.C.step[e];  // handed back at a step boundary
+    if (!kTrap && from == kReturned) step = a.C.step[e];  // handed back at a step boundary
     if (kInstr && a.trace_sites) {  // the trace continues where the previous launch stopped
       trace_base = a.trace_counts[e];  // may exceed the capacity: events beyond it are counted, not recorded
       trace = (leader && trace_base < a.trace_cap) ? a.trace_sites + (int64_t)e * a.trace_cap + trace_base : nullptr;
@@ -386,13 +386,13 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
   // events, cold: chain walks and step ends); it changes role only once, when all its lanes have run dry.
   // The lists a warp serves in its first and in its second role, four bits per list number:
   const uint32_t hot_lists = deep_on ? 0x23u : 0x234u, cold_lists = 0x10u;
-  const int      n_hot = deep_on ? 2 : 3, n_roles = (G > 1) ? 1 : 2;
+  const int      n_hot = deep_on ? 2 : 3, n_roles = kTrap ? 1 : 2;
   for (int role = 0; role < n_roles; ++role) {
     const bool     serve_hot = (role == 0) == hot_role;
     // round 2 of a launch serves what the other kernel handed over during round 1
-    const uint32_t serve = (G > 1) ? (a.round == 2 ? (uint32_t)kDeferred : (4u | ((uint32_t)kDeferred << 4)))
-                                   : a.round == 2 ? (uint32_t)kReturned : serve_hot ? hot_lists : cold_lists;
-    const int      n_serve = (G > 1) ? (a.round == 2 ? 1 : 2) : a.round == 2 ? 1 : serve_hot ? n_hot : 2;
+    const uint32_t serve = kTrap ? (a.round == 2 ? (uint32_t)kDeferred : (4u | ((uint32_t)kDeferred << 4)))
+                                 : a.round == 2 ? (uint32_t)kReturned : serve_hot ? hot_lists : cold_lists;
+    const int      n_serve = kTrap ? (a.round == 2 ? 1 : 2) : a.round == 2 ? 1 : serve_hot ? n_hot : 2;
     int64_t        e64 = 0;
     bool           have = take_exciton(a.q, leader, serve, n_serve, lane, lt_mask, e64, from);
     if (G > 1) {
@@ -594,10 +594,10 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
       CNTMC_SEG(L, 7);  // waiting for the other lanes of the warp to finish their events
       // trap solver: an exciton that ended a time step on a site that is no trap goes back to the lanes
       bool yield = walk_yield;
-      if (G > 1 && a.yield_on && did_step && !did_event && !finished && !L.stuck && !(hop_info(L, a.T).total >= a.deep_rate)) yield = true;
+      if (kTrap && a.yield_on && did_step && !did_event && !finished && !L.stuck && !(hop_info(L, a.T).total >= a.deep_rate)) yield = true;
       finished = have && (finished || walk_finished || L.stuck);
       // lanes: landed in a deep trap, the trap solver takes over
-      const bool defer = (G == 1) && deep_on && did_event && !finished && L.hop_valid && L.hop.total >= a.deep_rate;
+      const bool defer = !kTrap && deep_on && did_event && !finished && L.hop_valid && L.hop.total >= a.deep_rate;
       const bool release = finished || defer || yield;
       if (__any_sync(kFullMask, release)) {
         int cls = 0;
@@ -620,8 +620,8 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
           if (finished) cls = activity_class(hop_info(L, a.T).total * a.dt, a.deep_thr);
         }
         file_excitons(a.q, finished && leader, cls, e, lane, lt_mask);
-        if (G == 1 && deep_on) hand_over(a.q, 0, defer, e, lane, lt_mask);
-        if (G > 1 && a.yield_on) hand_over(a.q, 1, yield && leader, e, lane, lt_mask);
+        if (!kTrap && deep_on) hand_over(a.q, 0, defer, e, lane, lt_mask);
+        if (kTrap && a.yield_on) hand_over(a.q, 1, yield && leader, e, lane, lt_mask);
         bool got = take_exciton(a.q, release && leader, serve, n_serve, lane, lt_mask, e64, from);
         if (G > 1) {
           got = __shfl_sync(kFullMask, got ? 1 : 0, gbase) != 0;
@@ -682,13 +682,20 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
   // The displacement accumulator and the position at the start of the step are only touched when a time step ends;
   // they live in shared memory (one slot per thread) so that the event path does not carry 12 registers of them.
   __shared__ double s_delta[3][128], s_old[3][128];
-  hop_loop<Draws, kInstr, 1, kDefer>(a, s_delta, s_old);
+  hop_loop<Draws, kInstr, 1, kDefer, false>(a, s_delta, s_old);
 }
 // the trap solver: class 4 of the previous launch and the excitons kubo_kernel deferred in this one
 template <bool kInstr>
 __global__ void __launch_bounds__(128, 4) deep_kernel(const KuboArgs a) {
   __shared__ double s_delta[3][128], s_old[3][128];
-  hop_loop<PhiloxDraws, kInstr, kGroup, false>(a, s_delta, s_old);
+  hop_loop<PhiloxDraws, kInstr, kGroup, false, true>(a, s_delta, s_old);
+}
+// the same lists served one exciton per lane by the generic loop: warps that hold trapped excitons only (experiment, option
+// deep_group = 1)
+template <bool kInstr>
+__global__ void __launch_bounds__(128, 5) trap_lanes_kernel(const KuboArgs a) {
+  __shared__ double s_delta[3][128], s_old[3][128];
+  hop_loop<PhiloxDraws, kInstr, 1, false, true>(a, s_delta, s_old);
 }
 
 
@@ -1045,6 +1052,8 @@ struct CsrArgs {
   SiteRec*        site;       // rate fields of every record: total, 1/total, CSR row
   int32_t*        flags;
   unsigned long long* counters;
+  int32_t*        guard_sites;  // sites whose row holds a pair near a theta midpoint (first guard_cap of them)
+  int32_t         guard_cap;
 };
 
 // Enumerate the candidates of site i in the reference's order: the 27-cell stencil with x outermost and z innermost
@@ -1124,7 +1133,10 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
     for (int j = 0; j < kGuideBuckets; ++j) a.site[i].guide[j] = g8[j];
     top.store(a.site[i].top);
     if (d == 0) atomicOr(a.flags + FLAG_EMPTY_ROW, 1);
-    if (guard) atomicAdd(a.counters + CTR_GUARD, 1ULL);
+    if (guard) {
+      const unsigned long long k = atomicAdd(a.counters + CTR_GUARD, 1ULL);
+      if (k < (unsigned long long)a.guard_cap) a.guard_sites[k] = (int32_t)i;
+    }
   }
 }
 

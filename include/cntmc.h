@@ -149,7 +149,9 @@ int cntmc_csr_nnz(const cntmc_t* h, int64_t* nnz);
 int cntmc_get_csr(const cntmc_t* h, int64_t* row_ptr /* [N+1] */, int32_t* nbr /* [nnz] */, double* cum /* [nnz] */);
 /* one row of the table (tables of 1e9 entries are not read back whole): up to cap entries, *len = the row's length */
 int cntmc_get_csr_row(const cntmc_t* h, int64_t site, int64_t cap, int32_t* nbr, double* cum, int64_t* len);
-/* pairs whose theta fell within 1e-9 grid pitches of a grid midpoint (device acos vs glibc acos could disagree) */
+/* rows holding a pair whose theta fell within 1e-9 grid pitches of a grid midpoint, where the device's acos could pick
+ * another table index than glibc's: every such row was recomputed on the host with glibc's acos and patched in
+ * (expected count: 0; option guard_ppb widens the band, for tests) */
 int64_t cntmc_csr_midpoint_guards(const cntmc_t* h);
 double  cntmc_csr_build_seconds(const cntmc_t* h);
 

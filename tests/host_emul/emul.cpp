@@ -83,6 +83,7 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
     }
     RateTable R{e->table.theta.data(), e->table.z.data(), e->table.a1.data(), e->table.a2.data(), e->table.rates.data(),
                 (int32_t)e->table.theta.size(), (int32_t)e->table.z.size(), (int32_t)e->table.a1.size(), (int32_t)e->table.a2.size()};
+    R.guard_tol = 1e-9;
     grid_hint(R.theta, R.n_theta, &R.start[0], &R.inv_step[0]);  // as cntmc_api.cu does: evenly spaced grids are not scanned in full
     grid_hint(R.z, R.n_z, &R.start[1], &R.inv_step[1]);
     grid_hint(R.a1, R.n_a1, &R.start[2], &R.inv_step[2]);

@@ -28,7 +28,7 @@ def test_config_3_one_gpu_share_of_1e8_excitons():
     p0 = e.particles()
     msd = e.kubo_step(DT, 40)
     p1 = e.particles()
-    assert e.get_option("chunk_steps") == 64                      # no shortened launches at this population
+    assert e.get_option("dbg_last_chunk") == 40                   # the whole call in one launch: no shortening by the staging budget
     assert int(p1["ndraw"].astype(np.int64).sum()) == 3 * count + 2 * e.hops() + e.reinjections()
     assert e.hops() > 0.3 * 40 * count
     off = np.abs(p1["delta"] - (p1["pos"] - p0["pos"])).max(axis=0) > 1e-18
@@ -114,3 +114,41 @@ def test_config_5_one_gpu_share_of_1e9_excitons():
             assert pop[s, k] - pop[s - 1, k] == cur[s, k - 1] - cur[s, k], (s, k)
     # alive after the call = counted in the last iteration, minus both contact slabs, plus the fresh contact population
     assert e.number_of_particles() == pop[-1].sum() - pop[-1, 0] - pop[-1, -1] + sc.c1_pop + sc.c2_pop
+
+
+def test_ten_million_site_film():
+    """Mesh ingestion at scale: 40 000 tubes x 250 sites = 1e7 sites at C4's density, ~2.8e9 table
+    entries (45 GB of rows).  Site records, geometry copies and row offsets are made on the device; sampled rows must be the
+    oracle's bits and a short run must account for every draw."""
+    import time
+    cfg = dict(film.CONFIG_FILMS["C4"])
+    cfg["NT"], cfg["LX"] = 2 * cfg["NT"], cfg["LX"] * 2 ** 0.5
+    pos, ori = film.film(**cfg)
+    mc = base_mc()
+    e = Engine(mc)
+    e.set_mesh(pos, ori)
+    t0 = time.time()
+    e.kubo_init()
+    init_s = time.time() - t0
+    N = e.num_sites()
+    assert N == 10_000_000 and 2.4e9 < e.csr_nnz() < 4.29e9 and e.csr_midpoint_guards() == 0
+    assert init_s < 20 and e.csr_build_seconds() < 2.0
+    t = T1m.T1()
+    t.set_lazy_rates(True)
+    t.set_memo(True)
+    t.draws_philox(1)
+    t.kubo_init(mc, pos, ori)
+    rng = np.random.default_rng(9)
+    for i in np.concatenate([[0, N - 1], rng.integers(0, N, 62)]):
+        nbr, cum = e.csr_row(int(i))
+        ids, c = t.row(int(i))
+        assert np.array_equal(nbr, ids) and np.array_equal(cum, c), int(i)
+    P = 500_000
+    e.kubo_create_particles(P, seed=1)
+    e.kubo_step(DT, 32, want_msd=False)
+    p = e.particles()
+    assert int(p["ndraw"].astype(np.int64).sum()) == 3 * P + 2 * e.hops() + e.reinjections() and e.hops() > 0.2 * 32 * P
+    t.create_particles(48, first_global_id=1234)
+    t.kubo_step(DT, 32, want_msd=False)
+    pt = t.particles()
+    assert np.array_equal(pt["site"], p["site"][1234:1234 + 48])

@@ -111,7 +111,8 @@ def test_chunking_scheduling_and_occupancy_do_not_change_results():
                  dict(chunk_steps=8, hot_pct=0, deep_thr=16), dict(chunk_steps=3, hot_pct=100, deep_thr=16, deep_blocks=1),
                  dict(chunk_steps=8, hot_pct=30, occupancy=6, deep_thr=1, deep_blocks=2),
                  dict(top_entries=0), dict(top_entries=1, chunk_steps=16, deep_thr=0), dict(top_entries=0, runs=0, hot_pct=50),
-                 dict(dirs=0, chunk_steps=9, deep_thr=30), dict(chunk_steps=40, deep_thr=2, deep_rounds=2), dict(chunk_steps=64, deep_thr=9, deep_rounds=1), dict(runs=0, hot_pct=5, chunk_steps=33, deep_thr=16)):
+                 dict(dirs=0, chunk_steps=9, deep_thr=30), dict(chunk_steps=40, deep_thr=2, deep_rounds=2), dict(chunk_steps=64, deep_thr=9, deep_rounds=1),
+                 dict(chunk_steps=64, deep_thr=8, deep_group=1), dict(chunk_steps=11, deep_thr=16, deep_group=1, deep_rounds=1), dict(runs=0, hot_pct=5, chunk_steps=33, deep_thr=16)):
         e = Engine(mc)
         e.set_mesh(pos, ori)
         for k, v in opts.items():
@@ -313,3 +314,22 @@ def test_a_new_population_can_follow_a_failed_replay(golden_small):
     e.kubo_create_particles(50, seed=3)
     e.kubo_step(g.dt, 20)
     assert e.hops() > 0
+
+
+def test_rows_next_to_a_theta_midpoint_are_recomputed_with_glibc(golden):
+    """The one place where the device's libm could change a table index relative to the reference is an acos that lands on
+    a grid midpoint.  Such rows are recomputed on the host with glibc's acos and patched in.  None occurs on any film
+    here, so the band is widened (option guard_ppb: 0.03 grid pitches instead of 1e-9) to exercise the repair: hundreds of
+    rows go through the host path, and the table is still the reference's, bit for bit."""
+    e = Engine(golden.mc)
+    e.set_mesh(golden.pos_nm, golden.orient)
+    e.set_option("guard_ppb", 30_000_000)
+    e.kubo_init()
+    assert e.csr_midpoint_guards() > 50 and e.get_option("dbg_midpoint_repairs") == e.csr_midpoint_guards()
+    assert e.get_option("dbg_midpoint_changed") == 0              # the device's acos picked the same indices as glibc's
+    row_ptr, nbr, cum = e.csr()
+    assert np.array_equal(row_ptr, golden.z["row_ptr"]) and np.array_equal(nbr, golden.z["nbr"]) and np.array_equal(cum, golden.z["cum"])
+    plain = Engine(golden.mc)
+    plain.set_mesh(golden.pos_nm, golden.orient)
+    plain.kubo_init()
+    assert plain.csr_midpoint_guards() == 0
