@@ -42,6 +42,8 @@ SIGNATURES = {
     "cntmc_crossings": (I64, [V]),
     "cntmc_probes": (I64, [V]),
     "cntmc_init": (C.c_int, [V, I64, I64, U64, I64]),
+    "cntmc_init_replay": (C.c_int, [V, I64, I64, I64, V, V, V]),
+    "cntmc_get_gids": (C.c_int, [V, V]),
     "cntmc_step": (C.c_int, [V, D, I64, V, V]),
     "cntmc_step_dev": (C.c_int, [V, D, I64, V]),
     "cntmc_get_area": (C.c_int, [V, V]),

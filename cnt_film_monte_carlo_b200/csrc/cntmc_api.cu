@@ -167,6 +167,7 @@ struct cntmc_handle {
   DevBuf<int64_t>  r_off;
   DevBuf<int32_t>  r_draws;
   DevBuf<double>   r_logs;
+  int64_t          replay_ids = 0;  // contact replay: ids covered by the draw lists
 
   // reductions, diagnostics
   DevBuf<double>             d_partial, d_sums;
@@ -1168,7 +1169,8 @@ int64_t cntmc_crossings(const cntmc_t* h) { return h->crossings; }
 int64_t cntmc_probes(const cntmc_t* h) { return h->probes; }
 
 // ---- contact flavour ----------------------------------------------------------------------------------------------------
-int cntmc_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_t capacity) {
+static int contact_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_t capacity, int64_t n_ids,
+                        const int64_t* offsets, const int32_t* draws_in, const double* logs) {
   return guarded(h, [&] {
     require(h->prm.n_seg >= 2, "\"number of segments\" must be at least 2 in contact mode");
     require(c1_pop >= 0 && c2_pop >= 0, "contact populations must be non-negative");
@@ -1185,10 +1187,23 @@ int cntmc_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_
     h->d_c2.upload(h->c2_sites, st);
     h->c1_pop = c1_pop;
     h->c2_pop = c2_pop;
-    h->replay = false;
+    h->replay = offsets != nullptr;
     h->draws = DrawConfig{};
     h->draws.seed = seed;
     h->draws.first_gid = (uint64_t)h->opt_gid_base << 56;  // several handles of one simulation keep their stream ids apart
+    if (h->replay) {  // recorded draws per exciton id (ids in order of birth, as the kernels number them)
+      require(n_ids > 0 && draws_in != nullptr, "bad replay arguments");
+      use_device(h);
+      const size_t total = (size_t)offsets[n_ids];
+      h->r_off.upload(offsets, (size_t)n_ids + 1, st);
+      h->r_draws.upload(draws_in, total, st);
+      if (logs) h->r_logs.upload(logs, total, st);
+      h->draws.first_gid = 0;
+      h->draws.replay_off = h->r_off.p;
+      h->draws.replay_draws = h->r_draws.p;
+      h->draws.replay_logs = logs ? h->r_logs.p : nullptr;
+      h->replay_ids = n_ids;
+    }
     // create_particles (monte_carlo.h:274-316): linear profile over the slabs, sites from the half-open slab lists
     const double         dp = double(c2_pop - c1_pop) / (double(n_seg) - 1);
     std::vector<int64_t> count_off((size_t)n_seg + 1, 0), site_off((size_t)n_seg + 1, 0);
@@ -1226,13 +1241,28 @@ int cntmc_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_
       a.n_seg = n_seg;
       a.alive = h->d_alive.p;
       a.flags = h->d_flags.p;
-      create_contact_population_kernel<PhiloxDraws><<<(unsigned)((P0 + 255) / 256), 256, 0, st>>>(a);
+      if (h->replay)
+        create_contact_population_kernel<ReplayDraws><<<(unsigned)((P0 + 255) / 256), 256, 0, st>>>(a);
+      else
+        create_contact_population_kernel<PhiloxDraws><<<(unsigned)((P0 + 255) / 256), 256, 0, st>>>(a);
       CUDA_CHECK(cudaGetLastError());
       check_flags(h);  // synchronises before the temporaries go away
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     h->initialised = true;
   });
+}
+
+int cntmc_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_t capacity) {
+  return contact_init(h, c1_pop, c2_pop, seed, capacity, 0, nullptr, nullptr, nullptr);
+}
+int cntmc_init_replay(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, int64_t n_ids, const int64_t* offsets, const int32_t* draws,
+                      const double* logs) {
+  if (!offsets || !draws || n_ids <= 0) {
+    h->err = "bad replay arguments";
+    return CNTMC_ERR_INVALID;
+  }
+  return contact_init(h, c1_pop, c2_pop, 0, 0, n_ids, offsets, draws, logs);
 }
 
 // nsteps iterations of { step ; metrics ; repopulate_contacts } -> dev_bins[nsteps][2*n_seg-1] (device, 64-bit counts)
@@ -1288,11 +1318,16 @@ static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned 
     a.flags = h->d_flags.p;
     a.counters = h->d_counters.p;
     const size_t smem = (size_t)n * nb * sizeof(int);
-    switch (h->opt_occupancy) {
-      case 4: contact_kernel<PhiloxDraws, 4><<<grid, 128, smem, st>>>(a); break;
-      case 6: contact_kernel<PhiloxDraws, 6><<<grid, 128, smem, st>>>(a); break;
-      case 8: contact_kernel<PhiloxDraws, 8><<<grid, 128, smem, st>>>(a); break;
-      default: contact_kernel<PhiloxDraws, 5><<<grid, 128, smem, st>>>(a); break;
+    if (h->replay) {  // the reference's own rand() stream, split per exciton id: every id born in this call needs its list
+      if ((int64_t)(h->next_gid + (uint64_t)((int64_t)n * C)) > h->replay_ids)
+        throw ReplayError("the replayed draw lists do not cover the excitons this call creates");
+      contact_kernel<ReplayDraws, 5><<<grid, 128, smem, st>>>(a);
+    } else {
+      switch (h->opt_occupancy) {
+        case 4: contact_kernel<PhiloxDraws, 4><<<grid, 128, smem, st>>>(a); break;
+        case 6: contact_kernel<PhiloxDraws, 6><<<grid, 128, smem, st>>>(a); break;
+        default: contact_kernel<PhiloxDraws, 5><<<grid, 128, smem, st>>>(a); break;
+      }
     }
     CUDA_CHECK(cudaGetLastError());
     // survivors, in work-item order, move to the front of the spare copy
@@ -1565,6 +1600,15 @@ int cntmc_get_particles(const cntmc_t* h, int32_t* site, double* pos, double* de
     if (heading) h->ex.heading.download(heading, n, st);
     if (ndraw) h->ex.ndraw.download(ndraw, n, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int cntmc_get_gids(const cntmc_t* h, uint64_t* gid) {
+  return guarded(h, [&] {
+    require(h->contact_mode && h->P > 0 && gid != nullptr, "exciton ids exist in contact mode only");
+    use_device(h);
+    h->ex.gid.download(gid, (size_t)h->P, h->stream);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
   });
 }
 

@@ -169,6 +169,18 @@ class Engine:
     def number_of_segments(self) -> int:
         return self.L.cntmc_number_of_segments(self.h)
 
+    def init_replay(self, c1_pop: int, c2_pop: int, offsets, draws, logs=None):
+        """monte_carlo::init with the reference's recorded draws per exciton id (ids in order of birth)"""
+        off = np.ascontiguousarray(offsets, np.int64)
+        dr = np.ascontiguousarray(draws, np.int32)
+        lg = None if logs is None else np.ascontiguousarray(logs, np.float64)
+        self._ck(self.L.cntmc_init_replay(self.h, c1_pop, c2_pop, len(off) - 1, _p(off), _p(dr), None if lg is None else _p(lg)))
+
+    def gids(self) -> np.ndarray:
+        g = np.empty(self.number_of_particles(), np.uint64)
+        self._ck(self.L.cntmc_get_gids(self.h, _p(g)))
+        return g
+
     def step(self, dt: float, nsteps: int = 1):
         n = self.number_of_segments()
         pop, cur = np.empty((nsteps, n), np.int64), np.empty((nsteps, n - 1), np.int64)

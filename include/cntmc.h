@@ -114,6 +114,14 @@ int64_t cntmc_probes(const cntmc_t* h);
 /* monte_carlo::init  monte_carlo.h:157-195 (contacts = first and last of "number of segments" slabs along y;
  * create_particles :274-316 with a linear profile from c1_pop to c2_pop; the reference hard-codes 1100 and 0). */
 int cntmc_init(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, uint64_t seed, int64_t capacity);
+/* same, with every draw taken from recorded lists (the reference's own rand() stream, split per exciton): exciton id g --
+ * ids in order of birth: the initial population in creation order, then per iteration the excitons repopulate creates on
+ * contact 1, then on contact 2 (monte_carlo.h:443-491) -- consumes draws[offsets[g] .. offsets[g+1]).  logs as in
+ * cntmc_kubo_create_particles_replay.  n_ids must cover every exciton created while stepping. */
+int cntmc_init_replay(cntmc_t* h, int64_t c1_pop, int64_t c2_pop, int64_t n_ids, const int64_t* offsets, const int32_t* draws,
+                      const double* logs);
+/* ids of the excitons alive, in the order of cntmc_get_particles (contact mode) */
+int cntmc_get_gids(const cntmc_t* h, uint64_t* gid);
 /* nsteps x { monte_carlo::step(dt) :343-355 ; save_population_profile :566-573 ; save_currents :593-636 ;
  * repopulate_contacts :443-455 }.  pop_out [nsteps][n_seg] excitons per slab, curr_out [nsteps][n_seg-1] net
  * crossings per interface (raw counts; the shim divides by area*dy and area*dt like the reference's writers). */

@@ -188,6 +188,31 @@ class T0:
     def contact_iteration(self, dt: float) -> None:
         self.L.t0_contact_iteration(dt)
 
+    def open_contacts_logged(self, json_path: str, seed: int = 100) -> int:
+        """monte_carlo::init with the creation draws attributed per exciton; returns the initial population."""
+        self.L.t0_open_contacts_logged.restype = C.c_int64
+        self.L.t0_contacts_attribute_creation.restype = C.c_int64
+        if self.L.t0_open_contacts_logged(json_path.encode(), seed) != 0:
+            raise RuntimeError(self.L.t0_last_error().decode())
+        p0 = self.L.t0_contacts_attribute_creation()
+        if p0 < 0:
+            raise RuntimeError(self.L.t0_last_error().decode())
+        return p0
+
+    def contact_iteration_logged(self, dt: float) -> None:
+        """step / save_metrics / repopulate_contacts with every draw attributed to the exciton (id = order of birth)"""
+        self.L.t0_contact_iteration_logged.argtypes = [C.c_double]
+        self.L.t0_contact_iteration_logged(dt)
+
+    def next_id(self) -> int:
+        self.L.t0_next_id.restype = C.c_int64
+        return self.L.t0_next_id()
+
+    def particle_ids(self):
+        ids = np.empty(self.L.t0_num_particles(), np.int64)
+        self.L.t0_particle_ids(_p(ids))
+        return ids
+
     def track_particle(self, dt: float, file_no: int, log_slot: int = 0) -> None:
         """monte_carlo::track_particle (monte_carlo.h:786-818); writes particle_path.<file_no>.dat in the output directory."""
         self.L.t0_track_particle.argtypes = [C.c_double, C.c_int, C.c_int64]

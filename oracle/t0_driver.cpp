@@ -13,7 +13,10 @@
 //     (SURVEY.md App. A.7);
 //   * t0_kubo_step_logged(): the 12-line particle loop of monte_carlo::kubo_step (monte_carlo.cpp:319-342) written
 //     out so the consuming exciton is known for every draw; it calls the reference's particle::step,
-//     update_delta_pos etc.  tests/test_oracle_t0.py proves it equal, bit for bit, to the verbatim kubo_step().
+//     update_delta_pos etc.  tests/test_oracle_t0.py proves it equal, bit for bit, to the verbatim kubo_step();
+//   * t0_contact_iteration_logged(): monte_carlo::step and monte_carlo::repopulate (monte_carlo.h:343-355, 458-491) written
+//     out with an id carried along every particle through repopulate's swaps, so that the draws of the contact loop are
+//     known per exciton (ids in order of birth); the same test proves it equal to the verbatim loop.
 #include <array>
 #include <cassert>
 #include <cstdint>
@@ -53,6 +56,9 @@ int64_t                           g_cur = -1;  // exciton currently consuming dr
 std::vector<std::vector<int32_t>> g_draws;     // per exciton, in consumption order
 int64_t                           g_total_draws = 0;
 int                               g_threads = 1;  // OpenMP team size for the reference's parallel regions
+std::vector<int32_t>              g_seq;          // draws of a stretch whose consumers are known by position (g_cur == -2)
+std::vector<int64_t>              g_ids;          // contact mode: id (order of birth) of _particle_list[i]
+int64_t                           g_next_id = 0;
 
 struct cout_silencer {
   std::streambuf* old;
@@ -75,6 +81,7 @@ extern "C" int rand(void) {
   const int r = (int)random();
   __atomic_fetch_add(&g_total_draws, 1, __ATOMIC_RELAXED);
   if (g_log_on && g_cur >= 0) g_draws[g_cur].push_back(r);
+  if (g_log_on && g_cur == -2) g_seq.push_back(r);
   return r;
 }
 
@@ -120,13 +127,41 @@ int t0_open_contacts(const char* json_path, unsigned seed) {
     g_sim.reset(new mc::monte_carlo(json_mc));
     g_sim->_time = 0;
     g_draws.clear();
-    g_cur = -1;
+    g_cur = g_log_on ? -2 : -1;  // logging: the creation draws go to g_seq (see t0_contacts_attribute_creation)
     g_sim->init();
+    g_cur = -1;
     return 0;
   } catch (const std::exception& e) {
     g_error = e.what();
     return -1;
   }
+}
+
+// the same, with the creation draws of the initial population attributed: create_particles (monte_carlo.h:274-316) draws,
+// per particle and in list order, a site, a free-flight time (again while the draw is zero) and a heading.  Returns the
+// population, or -1 (also when a zero draw makes the positions ambiguous -- pick another seed).
+int64_t t0_open_contacts_logged(const char* json_path, unsigned seed) {
+  g_log_on = true;
+  g_seq.clear();
+  if (t0_open_contacts(json_path, seed) != 0) return -1;
+  return 0;
+}
+int64_t t0_contacts_attribute_creation() {
+  const int64_t P0 = (int64_t)g_sim->_particle_list.size();
+  if ((int64_t)g_seq.size() != 3 * P0) {
+    g_error = "creation consumed " + std::to_string(g_seq.size()) + " draws for " + std::to_string(P0) + " particles";
+    return -1;
+  }
+  g_draws.assign((size_t)P0, {});
+  g_ids.resize((size_t)P0);
+  for (int64_t i = 0; i < P0; ++i) {
+    g_draws[(size_t)i].assign(g_seq.begin() + 3 * i, g_seq.begin() + 3 * i + 3);
+    g_ids[(size_t)i] = i;
+  }
+  g_next_id = P0;
+  g_seq.clear();
+  g_cur = -1;
+  return P0;
 }
 
 void t0_close() { g_sim.reset(); }
@@ -374,6 +409,59 @@ void t0_contact_iteration(double dt) {
   g_sim->step(dt);
   g_sim->save_metrics(dt);
   g_sim->repopulate_contacts();
+}
+// The same iteration with every draw attributed to the exciton that consumed it.  monte_carlo::step (monte_carlo.h:343-355)
+// in list order (= OMP_NUM_THREADS=1), save_metrics verbatim, then repopulate_contacts (:443-455) with repopulate's list
+// surgery (:458-491) written out so that g_ids follows every swap; a particle born here gets the next id.
+static void repopulate_logged(const double ymin, const double ymax, const unsigned n_particle, const std::vector<const mc::scatterer*>& s_list) {
+  auto&    p_list = g_sim->_particle_list;
+  unsigned j = p_list.size();
+  for (unsigned i = 0; i < j;) {
+    if (p_list[i].pos(1) >= ymin && p_list[i].pos(1) <= ymax) {
+      --j;
+      std::swap(p_list[i], p_list[j]);
+      std::swap(g_ids[i], g_ids[j]);
+    } else {
+      ++i;
+    }
+  }
+  unsigned       n = 0;
+  const unsigned final_size = j + n_particle;
+  const unsigned j_lim = std::min(int(p_list.size()), int(final_size));
+  for (; j < j_lim; ++j) {
+    g_ids[j] = g_next_id++;
+    attribute_to(g_ids[j]);
+    const int dice = std::rand() % s_list.size();
+    p_list[j] = mc::particle(s_list[dice]->pos(), s_list[dice], g_sim->_particle_velocity);
+    ++n;
+  }
+  for (; n < n_particle; ++n) {
+    g_ids.push_back(g_next_id++);
+    attribute_to(g_ids.back());
+    const int dice = std::rand() % s_list.size();
+    p_list.emplace_back(mc::particle(s_list[dice]->pos(), s_list[dice], g_sim->_particle_velocity));
+  }
+  p_list.resize(final_size);
+  g_ids.resize(final_size);
+  g_cur = -1;
+}
+void t0_contact_iteration_logged(double dt) {
+  cout_silencer quiet;
+  auto&         sim = *g_sim;
+  for (unsigned i = 0; i < sim._particle_list.size(); ++i) {
+    attribute_to(g_ids[i]);
+    sim._particle_list[i].step(dt, sim._all_scat_list, sim._max_hopping_radius);
+  }
+  g_cur = -1;
+  sim._time += dt;
+  sim.save_metrics(dt);
+  const double ymin = sim._domain.first(1), ymax = sim._domain.second(1), dy = (ymax - ymin) / double(sim._n_seg);
+  repopulate_logged(ymin, ymin + dy, sim._c1_pop, sim._c1_scat);
+  repopulate_logged(ymin + double(sim._n_seg - 1) * dy, ymax, sim._c2_pop, sim._c2_scat);
+}
+int64_t t0_next_id() { return g_next_id; }
+void    t0_particle_ids(int64_t* ids) {
+  for (size_t i = 0; i < g_ids.size(); ++i) ids[i] = g_ids[i];
 }
 // monte_carlo::track_particle (monte_carlo.h:786-818), verbatim; every draw is attributed to exciton `log_slot`
 void t0_track_particle(double dt, int file_no, int64_t log_slot) {

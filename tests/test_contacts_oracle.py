@@ -69,3 +69,20 @@ def test_track_particle_reproduces_reference_file(golden_small):
     assert format_path(path) == bytes(g.z["track_file"]).decode()
     extra, _ = t.track_particle(float(g.z["track_dt"]), gid=0, max_steps=len(path) - 1)
     assert len(extra) == len(path) - 1 and np.array_equal(extra, path[:-1])
+
+
+def test_contact_replay_fixture_is_reproduced_by_the_oracle(golden_small):
+    """The per-exciton draw lists of the reference's contact loop (ids in order of birth) replayed by the oracle: the same
+    survivors in the same states -- this is the fixture the GPU replays in tests/test_gpu_contacts.py."""
+    import os
+    g = golden_small
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_forster_contacts_replay.npz"))
+    t = T1m.T1()
+    t.draws_replay(z["draw_off"], z["draws"])
+    t.contacts_init(g.mc, g.pos_nm, g.orient, c1_pop=int(z["c1_pop"]), c2_pop=int(z["c2_pop"]))
+    for _ in range(int(z["iterations"])):
+        t.contact_iteration(float(z["dt"]))
+    p = t.particles()
+    assert not t.replay_exhausted()
+    # T1 keeps the reference's list order (the same swaps), so the lists compare position by position
+    assert np.array_equal(p["site"], z["site"]) and np.array_equal(p["pos"], z["pos"]) and np.array_equal(p["ff"], z["ff"])

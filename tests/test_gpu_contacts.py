@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from cnt_film_monte_carlo_b200 import film
-from cnt_film_monte_carlo_b200.engine import Engine
+from cnt_film_monte_carlo_b200.engine import CntmcError, Engine
 from oracle import t1 as T1m
 from conftest import base_mc
 
@@ -120,3 +120,38 @@ def test_mirror_writes_statistics_and_path_files(golden_small, tmp_path):
     y_last = float(rows[-1].split()[1])
     assert y_last >= dom[1] + 0.9 * (dom[4] - dom[1]) and all(float(r.split()[1]) < dom[1] + 0.9 * (dom[4] - dom[1]) for r in rows[:-1])
     sim.close()
+
+
+def test_contact_loop_replays_the_reference_draws(golden_small):
+    """monte_carlo::init, then 12 x { step ; save_metrics ; repopulate_contacts } with the reference's own rand() stream,
+    split per exciton (ids in order of birth; tests/golden/make_golden_contacts.py): every surviving exciton ends on the
+    reference's site with the reference's position, free-flight time and heading, bit for bit, and the integer bins
+    reproduce the reference's population_profile.dat and region_current.dat."""
+    import os
+    g = golden_small
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_forster_contacts_replay.npz"))
+    e = Engine(g.mc)
+    e.set_mesh(g.pos_nm, g.orient)
+    e.init_replay(int(z["c1_pop"]), int(z["c2_pop"]), z["draw_off"], z["draws"], z["draw_logs"])
+    assert e.number_of_particles() == int(z["p0"])
+    n_it, dt = int(z["iterations"]), float(z["dt"])
+    pop_a, cur_a = e.step(dt, 5)                 # several iterations per launch, and a second call
+    pop_b, cur_b = e.step(dt, n_it - 5)
+    pop, cur = np.concatenate([pop_a, pop_b]), np.concatenate([cur_a, cur_b])
+    p, ids = e.particles(), e.gids().astype(np.int64)
+    order, ref_order = np.argsort(ids), np.argsort(z["ids"])
+    assert np.array_equal(ids[order], z["ids"][ref_order])                       # the same excitons survive
+    assert np.array_equal(p["site"][order], z["site"][ref_order])
+    assert np.array_equal(p["pos"][:, order], z["pos"][:, ref_order])
+    assert np.array_equal(p["ff"][order], z["ff"][ref_order])
+    assert np.array_equal(p["heading"][order].astype(np.int32), z["heading"][ref_order])
+    n_seg = e.number_of_segments()
+    area, dom = e.area(), e.domain()
+    dy = (dom[4] - dom[1]) / n_seg
+    rows = lambda text, n: np.array([[float(v) for v in ln.split(",")] for ln in text.splitlines() if ln and ln[0] in "+-"]).reshape(-1, n + 1)
+    pop_ref, cur_ref = rows(bytes(z["pop_file"]).decode(), n_seg), rows(bytes(z["curr_file"]).decode(), n_seg - 1)
+    assert np.allclose(pop / (area * dy), pop_ref[:, 1:], rtol=2e-6, atol=0)    # the files carry 7 significant digits
+    assert np.allclose(cur / ((area[:-1] + area[1:]) / 2 * dt), cur_ref[:, 1:], rtol=2e-6, atol=0)
+    with pytest.raises(CntmcError) as ei:                                       # the lists end with the recorded run
+        e.step(dt, 1)
+    assert ei.value.code == -4
