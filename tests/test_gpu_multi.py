@@ -63,9 +63,9 @@ def test_multi_contacts_conserve_and_match_single_gpu_statistics(devices):
     if len(devices) == 1:
         assert np.array_equal(pop, pop1) and np.array_equal(cur, cur1)
     else:  # other streams, same ensemble: the contact slabs hold exactly what repopulate_contacts puts there
-        assert np.array_equal(pop[:, 0] >= 901, np.ones(30, bool)) and pop.sum(axis=1).min() > 0
+        assert np.all(pop[:, 0] > 0.8 * 901) and np.all(pop[:, 0] <= 901 + 100) and pop.sum(axis=1).min() > 0
         assert abs(pop.sum(axis=1).mean() - pop1.sum(axis=1).mean()) < 0.05 * pop1.sum(axis=1).mean()
-    assert m.number_of_particles() == pop[-1].sum() - 0 or m.number_of_particles() > 0
+    assert m.number_of_particles() == pop[-1].sum() - pop[-1, 0] - pop[-1, -1] + 901 + 100
 
 
 def test_cpp_driver_on_two_gpus_writes_the_same_rows(tmp_path):
