@@ -553,8 +553,8 @@ def run_contacts(args, rank, world, local_rank):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         pop, cur = eng.step(dt, n_int)
-        if world > 1:
-            sc.bins(np.concatenate([pop, cur], axis=1))
+        if world > 1:   # whole-ensemble bins, as in the resident loop (NCCL reduces device tensors)
+            sc.bins(torch.from_numpy(np.concatenate([pop, cur], axis=1)).to(dev))
     sec = time.perf_counter() - t0
     e2e_local = torch.tensor([float(eng.hops() - h_before), sec], dtype=torch.float64, device=dev)
     if world > 1:

@@ -142,7 +142,8 @@ struct cntmc_handle {
   uint64_t              nnz = 0;
   DevBuf<uint64_t>      d_row_begin;  // [N+1]
   int64_t               midpoint_guards = 0, midpoint_repairs = 0, midpoint_changed = 0;
-  int64_t               opt_guard_ppb = 1;  // theta within this many 1e-9 grid pitches of a midpoint flags its row
+  int64_t               opt_guard_ppb = 1;
+  int64_t               opt_csr_warp = 1;  // table build, fill pass: one warp per row  // theta within this many 1e-9 grid pitches of a midpoint flags its row
   double                csr_seconds = 0;
 
   // device tables
@@ -459,7 +460,10 @@ void common_init(cntmc_t* h) {
   h->d_row.alloc((size_t)nnz);
   a.row_begin = h->d_row_begin.p;
   a.row = h->d_row.p;
-  csr_rows_kernel<true><<<grid, block, 0, st>>>(a);
+  if (h->opt_csr_warp)  // one warp per row (default); 0: the one-thread-per-row kernel, kept as the cross-check
+    csr_fill_warp_kernel<<<(unsigned)((N + 3) / 4), 128, 0, st>>>(a);
+  else
+    csr_rows_kernel<true><<<grid, block, 0, st>>>(a);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(h->ev1, st));
   int32_t            flags[FLAG_COUNT];
@@ -533,6 +537,7 @@ void common_init(cntmc_t* h) {
       CUDA_CHECK(cudaStreamSynchronize(st));
     }
   }
+  if (flags[FLAG_BAD_LINKS] & 2) throw StateError("table build: count pass and fill pass disagree on the length of a row");
   if (flags[FLAG_BAD_LINKS]) throw std::invalid_argument("chain links of the site list are not symmetric");
   if (flags[FLAG_EMPTY_ROW])
     throw StateError("a site has no neighbour inside the hopping radius (undefined behaviour in the reference, scatterer.h:91)");
@@ -1651,6 +1656,9 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "slice_share") {
       require(value >= 0 && value <= 16, "slice_share must be in [0, 16]");
       h->opt_slice_share = value;
+    } else if (k == "csr_warp") {
+      require(!h->initialised, "csr_warp must precede initialisation");
+      h->opt_csr_warp = value ? 1 : 0;
     } else if (k == "guard_ppb") {
       require(value >= 1 && value <= 1000000000, "guard_ppb must be in [1, 1e9]");
       require(!h->initialised, "guard_ppb must precede initialisation");
@@ -1704,6 +1712,7 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "deep_group") return h->opt_deep_group;
   if (k == "host_slices") return h->opt_host_slices;
   if (k == "guard_ppb") return h->opt_guard_ppb;
+  if (k == "csr_warp") return h->opt_csr_warp;
   if (k == "dbg_last_chunk") return h->last_chunk;
   if (k == "dbg_midpoint_repairs") return h->midpoint_repairs;
   if (k == "dbg_midpoint_changed") return h->midpoint_changed;

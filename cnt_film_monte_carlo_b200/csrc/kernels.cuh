@@ -1140,4 +1140,176 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
   }
 }
 
+// K1, fill pass, one WARP per site (round 2).  The one-thread-per-site kernel above spends 1.7e11 warp-instructions on C4 with
+// 10 of 32 lanes active: every lane walks its own cells and meets its accepted pairs at its own pace.  Here the 32 lanes test
+// 32 candidates of the current cell per instruction, the accepted ones are queued in candidate order in shared memory, and
+// every time 32 have gathered the warp evaluates their rates together (scatterer.cpp:44-63, all lanes converged), walks the
+// sequential FP64 prefix sum over them in order (scatterer.cpp:78-80: the same additions in the same order, one lane-value at
+// a time through a shuffle), writes the 32 entries as one coalesced 512-byte store and merges them into the row's three
+// widest entries (order: rate descending, row position ascending -- what TopEntries::add keeps).  The search guide is found
+// by eight lanes with a binary search each (first k with cum[k] > dice_min(j), else d-1: build_guide's scan, independently per
+// bucket, valid because cum is non-decreasing).  Same candidates, same order, same arithmetic: the same bits.
+struct TopKey {
+  double  rate, lo, hi;
+  int32_t nbr, pos;  // pos: position in the row (ties keep the earlier entry); INT32_MAX = empty
+};
+__device__ __forceinline__ bool top_before(double ra, int32_t pa, double rb, int32_t pb) { return ra > rb || (ra == rb && pa < pb); }
+__global__ void __launch_bounds__(128) csr_fill_warp_kernel(const CsrArgs a) {
+  __shared__ int32_t s_queue[4][64];
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int64_t  i = (int64_t)blockIdx.x * 4 + w;
+  if (i >= a.N) return;
+  int32_t*       queue = s_queue[w];
+  const SiteGeom s1 = a.geom[i];
+  const int      cx = cell_coord(s1.px, a.lo[0], a.radius), cy = cell_coord(s1.py, a.lo[1], a.radius),
+            cz = cell_coord(s1.pz, a.lo[2], a.radius);
+  const uint64_t base = a.row_begin[i];
+  const uint32_t want = (uint32_t)(a.row_begin[i + 1] - base);
+  uint32_t d = 0;
+  double   acc = 0.0;
+  bool     guard = false;
+  int      qcount = 0;
+  TopKey   top[kTopEntries];  // uniform over the warp
+#pragma unroll
+  for (int j = 0; j < kTopEntries; ++j) top[j] = TopKey{-1.0, 0.0, 0.0, -1, 0x7fffffff};
+
+  auto process = [&](int m) {  // the first m queued candidates (m <= 32), in order
+    double  rate = 0.0;
+    int32_t nbr = -1;
+    bool    g = false;
+    if (lane < m) {
+      const int32_t  qq = queue[lane];
+      const SiteGeom s2 = a.cell_geom[qq];
+      rate = pair_rate(s1, s2, a.R, &g);
+      nbr = a.cell_sites[qq];
+    }
+    guard |= __any_sync(kFullMask, g);
+    double cum = 0.0, below = 0.0;
+    for (int l = 0; l < m; ++l) {  // scatterer.cpp:78-80, sequential
+      const double r = __shfl_sync(kFullMask, rate, l);
+      const double b = (d + l == 0) ? -1.0 : acc;
+      acc = (d + l == 0) ? r : acc + r;
+      if (lane == l) {
+        cum = acc;
+        below = b;
+      }
+    }
+    if (lane < m) {
+      RowEntry en;
+      en.cum = cum;
+      en.nbr = nbr;
+      en.pad = 0;
+      a.row[base + d + lane] = en;
+    }
+    // the three widest of { current top } and { this batch }: three rounds of a warp-wide arg-best
+    bool taken = !(lane < m);
+    TopKey nt[kTopEntries];
+    int    used = 0;  // how many of the old top entries have been consumed (they are sorted)
+#pragma unroll
+    for (int j = 0; j < kTopEntries; ++j) {
+      double  br = taken ? -2.0 : rate;
+      int32_t bp = taken ? 0x7fffffff : (int32_t)(d + lane);
+      int     bl = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double  r2 = __shfl_xor_sync(kFullMask, br, o);
+        const int32_t p2 = __shfl_xor_sync(kFullMask, bp, o);
+        const int     l2 = __shfl_xor_sync(kFullMask, bl, o);
+        if (top_before(r2, p2, br, bp)) {
+          br = r2;
+          bp = p2;
+          bl = l2;
+        }
+      }
+      // best of the batch (uniform: br, bp, bl) against the next unused old entry
+      const bool have_new = br > -2.0 && bp != 0x7fffffff;
+      const bool old_wins = used < kTopEntries && top[used].pos != 0x7fffffff &&
+                            (!have_new || top_before(top[used].rate, top[used].pos, br, bp));
+      if (old_wins) {
+        nt[j] = top[used];
+        ++used;
+      } else if (have_new) {
+        nt[j].rate = br;
+        nt[j].pos = bp;
+        nt[j].lo = __shfl_sync(kFullMask, below, bl);
+        nt[j].hi = __shfl_sync(kFullMask, cum, bl);
+        nt[j].nbr = __shfl_sync(kFullMask, nbr, bl);
+        if (lane == bl) taken = true;
+      } else {
+        nt[j] = TopKey{-1.0, 0.0, 0.0, -1, 0x7fffffff};
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kTopEntries; ++j) top[j] = nt[j];
+    d += (uint32_t)m;
+  };
+
+  for (int c = 0; c < 27; ++c) {  // the reference's stencil order: x outermost, z innermost (monte_carlo.h:402-411)
+    const int ix = cx - 1 + c / 9, iy = cy - 1 + (c / 3) % 3, iz = cz - 1 + c % 3;
+    if (!(ix > -1 && ix < a.nb[0] && iy > -1 && iy < a.nb[1] && iz > -1 && iz < a.nb[2])) continue;
+    const int64_t b = (int64_t)ix + (int64_t)iy * a.nb[0] + (int64_t)iz * a.nb[0] * a.nb[1];
+    const int64_t q0 = a.cell_start[b], q1 = a.cell_start[b + 1];
+    for (int64_t q = q0; q < q1; q += 32) {
+      const bool in = q + lane < q1;
+      bool       ok = false;
+      if (in) ok = within_cutoff(s1, a.cell_geom[q + lane], a.radius);
+      const unsigned m = __ballot_sync(kFullMask, ok);
+      if (ok) queue[qcount + __popc(m & lt_mask)] = (int32_t)(q + lane);
+      qcount += __popc(m);
+      __syncwarp();
+      if (qcount >= 32) {
+        process(32);
+        const int32_t keep = (lane + 32 < qcount) ? queue[lane + 32] : 0;
+        __syncwarp();
+        if (lane + 32 < qcount) queue[lane] = keep;
+        qcount -= 32;
+        __syncwarp();
+      }
+    }
+  }
+  if (qcount > 0) process(qcount);
+
+  if (d != want) atomicOr(a.flags + FLAG_BAD_LINKS, 2);  // the two passes must agree on every row's length
+  // search guide: lane j < 8 finds the answer for the smallest dice of bucket j (hop_core.h build_guide)
+  __syncwarp();  // the row written by the other lanes is read below
+  const uint32_t sc = guide_scale(d);
+  uint32_t       gk = 0;
+  if (lane < kGuideBuckets && d > 0) {
+    const double dm = guide_dice_min(acc, lane);
+    uint32_t     lo = 0, hi = d - 1;  // first k with cum[k] > dm, else d-1
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (a.row[base + mid].cum > dm)
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    gk = lo >> sc;
+  }
+  __syncwarp();
+  uint32_t g8[kGuideBuckets];
+#pragma unroll
+  for (int j = 0; j < kGuideBuckets; ++j) g8[j] = __shfl_sync(kFullMask, gk, j);
+  if (lane == 0) {
+    SiteRec& r = a.site[i];
+    r.total = acc;                       // scatterer.h:91  _max_rate = neighbors.back().first
+    r.inv_total = d ? 1. / acc : 0.0;   // scatterer.h:92
+    r.row_begin = (uint32_t)base;
+    r.row_len = d;
+#pragma unroll
+    for (int j = 0; j < kGuideBuckets; ++j) r.guide[j] = (uint8_t)g8[j];
+    r.top.lo0 = top[0].lo; r.top.hi0 = top[0].hi;
+    r.top.lo1 = top[1].lo; r.top.hi1 = top[1].hi;
+    r.top.lo2 = top[2].lo; r.top.hi2 = top[2].hi;
+    r.top.nbr[0] = top[0].nbr; r.top.nbr[1] = top[1].nbr; r.top.nbr[2] = top[2].nbr;
+    r.top.pad = 0;
+    if (d == 0) atomicOr(a.flags + FLAG_EMPTY_ROW, 1);
+    if (guard) {
+      const unsigned long long k = atomicAdd(a.counters + CTR_GUARD, 1ULL);
+      if (k < (unsigned long long)a.guard_cap) a.guard_sites[k] = (int32_t)i;
+    }
+  }
+}
+
 }  // namespace cntmc

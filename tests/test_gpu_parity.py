@@ -333,3 +333,28 @@ def test_rows_next_to_a_theta_midpoint_are_recomputed_with_glibc(golden):
     plain.set_mesh(golden.pos_nm, golden.orient)
     plain.kubo_init()
     assert plain.csr_midpoint_guards() == 0
+
+
+def test_table_build_one_warp_per_row_equals_one_thread_per_row():
+    """The fill pass of the table build, one warp per row (default) against the one-thread-per-row kernel: every entry, every
+    site's rate fields, search guide and top entries (seen through a run with and without the shortcuts that read them)."""
+    pos, ori = film.film(NT=300, NP=250, a=2.0, LX=245.0, LY=100.0, seed=1234)   # C4's density: rows of several hundred entries
+    mc = base_mc()
+    out = []
+    for warp in (1, 0):
+        e = Engine(mc)
+        e.set_mesh(pos, ori)
+        e.set_option("csr_warp", warp)
+        e.kubo_init()
+        rp, nbr, cum = e.csr()
+        s = e.sites()
+        e.kubo_create_particles(4000, seed=6)
+        e.trace_enable(1 << 12)
+        msd = e.kubo_step(1e-13, 40)
+        counts, sites = e.trace()
+        out.append((rp, nbr, cum, s["max_rate"], s["inv_max_rate"], msd, counts, sites, e.particles(), e.get_option("dbg_top_events")))
+    a, b = out
+    assert np.diff(a[0]).max() > 400
+    for k in range(8):
+        assert np.array_equal(a[k], b[k]), k
+    assert all(np.array_equal(a[8][k], b[8][k]) for k in a[8]) and a[9] == b[9] and a[9] > 0
