@@ -1296,6 +1296,7 @@ static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned 
       for (int s = 0; s < n; ++s) h->time += dt;
       continue;
     }
+    require(W < (1ll << 32), "more than 2^32 excitons in one contact launch: lower chunk_steps");  // work items are 32-bit indices
     h->reserve_contact(W, h->P);
     const unsigned grid = (unsigned)std::min<int64_t>((W + 127) / 128, (int64_t)h->sm_count * h->opt_occupancy);
     set_u64_kernel<<<1, 1, 0, st>>>(h->d_counters.p + CTR_QUEUE, (unsigned long long)grid * 128ull);
@@ -1338,9 +1339,9 @@ static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned 
     // survivors, in work-item order, move to the front of the spare copy
     iota_kernel<<<(unsigned)((W + 255) / 256), 256, 0, st>>>(h->e_iota.p, W);
     size_t bytes = 0;
-    cub::DeviceSelect::Flagged(nullptr, bytes, h->e_iota.p, h->d_alive.p, h->e_perm.p, d_count.p, (int)W, st);
+    cub::DeviceSelect::Flagged(nullptr, bytes, h->e_iota.p, h->d_alive.p, h->e_perm.p, d_count.p, (int64_t)W, st);
     h->sort_tmp.alloc(bytes);
-    CUDA_CHECK(cub::DeviceSelect::Flagged(h->sort_tmp.p, bytes, h->e_iota.p, h->d_alive.p, h->e_perm.p, d_count.p, (int)W, st));
+    CUDA_CHECK(cub::DeviceSelect::Flagged(h->sort_tmp.p, bytes, h->e_iota.p, h->d_alive.p, h->e_perm.p, d_count.p, (int64_t)W, st));
     unsigned long long survivors = 0;
     d_count.download(&survivors, 1, st);
     check_flags(h);  // synchronises

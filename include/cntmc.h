@@ -180,6 +180,7 @@ int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites);
  *              from a register-resident window of site records (default 0 = off: bit-identical results, but slower on
  *              every workload measured so far); deep_blocks (blocks per SM of its launch, default 4), deep_rounds
  *              (2: it hands excitons that left their trap back to the lanes once per launch; default 2)
+ * csr_warp     1 (default): the table's fill pass runs one warp per row; 0: one thread per row (the cross-check)
  * host_slices  cntmc_kubo_step_host_state steps the uploaded population in this many slices on their own streams so that
  *              the copies of one overlap the kernels of the others (default 4; populations below 65536 per slice: 1)
  * gid_base_shift56  contact mode: stream ids start at value * 2^56 (cntmc_multi keeps the GPUs' streams apart with it)
