@@ -39,15 +39,15 @@ DT = 1e-13
 TRIM_WIDE = {"xlim": [-1e-5, 1e-5], "ylim": [-1e-5, 1e-5], "zlim": [-1e-5, 1e-5]}
 TRIM_INPUT_JSON = {"xlim": [-1e-6, 1e-6], "ylim": [0, 1e-7], "zlim": [-1e-6, 1e-6]}   # the reference's input.json:56-60
 WORKLOADS = {
-    "C1": dict(film="C1", mode="kubo", dt=1e-15, trim=TRIM_INPUT_JSON, excitons=2000, intervals=20000, chunk=4096, scaling="weak",
+    "C1": dict(film="C1", mode="kubo", dt=1e-15, trim=TRIM_INPUT_JSON, excitons=2000, intervals=20000, chunk=4096, steps=10, scaling="weak",
                text="C1: input.json verbatim (trim limits, dt 1e-15 s, 2000 excitons) on the 200-tube x 100-site stand-in film (seed 1234)"),
-    "C2": dict(film="C2", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=1_000_000, intervals=100, chunk=64, scaling="weak",
+    "C2": dict(film="C2", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=1_000_000, intervals=100, chunk=64, steps=145, scaling="weak",
                text="C2: 1000-tube x 100-site random CNT film (seed 1234), forster table 21x11x11x11, cutoff 20 nm"),
-    "C3": dict(film="C2", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=None, intervals=100, chunk=64, scaling="strong",
+    "C3": dict(film="C2", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=None, intervals=100, chunk=64, steps=5, scaling="strong",
                text="C3: C2 film, a fixed population (--excitons-total) split over the ranks by global id"),
-    "C4": dict(film="C4", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=1_000_000, intervals=64, chunk=64, scaling="weak",
+    "C4": dict(film="C4", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=1_000_000, intervals=64, chunk=64, steps=10, scaling="weak",
                text="C4: dense film, 20 000 tubes x 250 sites (5e6 sites, ~1.4e9 table entries), HBM-resident rate table"),
-    "C5": dict(film="C2", mode="contacts", dt=DT, trim=TRIM_WIDE, excitons=None, intervals=25, chunk=64, scaling="weak",
+    "C5": dict(film="C2", mode="contacts", dt=DT, trim=TRIM_WIDE, excitons=None, intervals=25, chunk=64, steps=5, scaling="weak",
                text="C5: contact-driven transport on the C2 film, contact population scaled to ~1.25e8 excitons alive per GPU"),
 }
 WORKLOAD = WORKLOADS["C2"]["text"]
@@ -603,7 +603,8 @@ def run_contacts(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=0,
+                    help="timed bench steps (0 = the workload's own; C2: 145 x 100 intervals = the config's 1e4 hops per exciton)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS), help="BASELINE.json config (C2 = the headline)")
@@ -622,6 +623,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=100.0, help="seconds of CPU work for the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps <= 0:
+        args.steps = WORKLOADS[args.workload]["steps"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
