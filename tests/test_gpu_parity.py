@@ -105,7 +105,7 @@ def test_chunking_scheduling_and_occupancy_do_not_change_results():
     pos, ori = film.film(NT=150, NP=60, a=5.0, LX=300.0, LY=80.0, seed=5)
     mc = base_mc()
     states, msds = [], []
-    # the first run is the plain loop (no group solver, no parking); every other scheduling must give the same bits
+    # the first run is the plain loop (no trap solver); every other scheduling must give the same bits
     for opts in (dict(chunk_steps=64, occupancy=6, deep_thr=0), dict(chunk_steps=7, occupancy=4, deep_thr=16), dict(chunk_steps=1, deep_thr=8, deep_rounds=1),
                  dict(chunk_steps=200, occupancy=5, deep_thr=0), dict(chunk_steps=64, stage_mb=1, deep_thr=16, deep_blocks=1),
                  dict(chunk_steps=8, hot_pct=0, deep_thr=16), dict(chunk_steps=3, hot_pct=100, deep_thr=16, deep_blocks=1),
