@@ -34,6 +34,7 @@ inline int hermitian_eig(int n, const std::complex<double>* A_in, double* w, std
     for (int p = 0; p < n; ++p)
       for (int q = p + 1; q < n; ++q) off += std::norm(at(p, q));
     if (std::sqrt(2 * off) <= 1e-17 * scale || off == 0) break;
+    int rotations = 0;
     for (int p = 0; p < n - 1; ++p) {
       for (int q = p + 1; q < n; ++q) {
         const cd     apq = at(p, q);
@@ -41,6 +42,13 @@ inline int hermitian_eig(int n, const std::complex<double>* A_in, double* w, std
         if (g == 0) continue;
         const double app = at(p, p).real(), aqq = at(q, q).real();
         if (g <= 1e-300) continue;
+        // an element that no longer registers against either diagonal entry is done
+        if (std::abs(app) + 100 * g == std::abs(app) && std::abs(aqq) + 100 * g == std::abs(aqq)) {
+          at(p, q) = cd(0, 0);
+          at(q, p) = cd(0, 0);
+          continue;
+        }
+        ++rotations;
         // rotation that zeroes A[p][q]: phase e = apq/|apq|, angle from tan(2 theta) = 2|apq| / (aqq - app)
         const cd     e = apq / g;
         const double tau = (aqq - app) / (2 * g);
@@ -67,6 +75,7 @@ inline int hermitian_eig(int n, const std::complex<double>* A_in, double* w, std
         at(q, q) = cd(at(q, q).real(), 0);
       }
     }
+    if (rotations == 0) break;
   }
   std::vector<int> order(n);
   std::iota(order.begin(), order.end(), 0);
