@@ -91,6 +91,19 @@ SIGNATURES = {
     "cntmc_multi_time": (D, [V]),
     "cntmc_multi_init": (C.c_int, [V, I64, I64, U64]),
     "cntmc_multi_step": (C.c_int, [V, D, I64, V, V]),
+    "cntmc_davoody_last_error": (CP, []),
+    "cntmc_tube_create": (V, [C.c_int, C.c_int, C.c_int]),
+    "cntmc_tube_destroy": (None, [V]),
+    "cntmc_tube_info": (C.c_int, [V, V, V]),
+    "cntmc_tube_exciton_dims": (C.c_int, [V, C.c_int, V]),
+    "cntmc_tube_exciton_energy": (C.c_int, [V, C.c_int, V]),
+    "cntmc_transfer_create": (V, [V, V, D, D, C.c_int]),
+    "cntmc_transfer_destroy": (None, [V]),
+    "cntmc_transfer_info": (C.c_int, [V, V, V]),
+    "cntmc_transfer_pair_factors": (C.c_int, [V, V, V, V]),
+    "cntmc_transfer_first_order": (C.c_int, [V, I64, V, V, V, V, V]),
+    "cntmc_transfer_table": (C.c_int, [V, V, V, V, V, V, V]),
+    "cntmc_create_davoody_table": (C.c_int, [V, V, V, V, V, V, V]),
 }
 
 _lib = None

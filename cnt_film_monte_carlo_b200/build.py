@@ -17,8 +17,9 @@ CSRC = os.path.join(HERE, "csrc")
 CPP = os.path.join(HERE, "cpp")
 LIB = os.path.join(HERE, "libcntmc.so")
 DRIVER = os.path.join(HERE, "cntmc_main")
-SOURCES = ["cntmc_api.cu", "cntmc_multi.cu", "host_setup.cpp"]
-HEADERS = ["hop_core.h", "fast_log.h", "log_table.inc", "csr_core.h", "kernels.cuh", "host_setup.h", "json_min.h"]
+SOURCES = ["cntmc_api.cu", "cntmc_multi.cu", "cntmc_davoody.cu", "host_setup.cpp"]
+HEADERS = ["hop_core.h", "fast_log.h", "log_table.inc", "csr_core.h", "kernels.cuh", "host_setup.h", "json_min.h",
+           "herm_eig.h", "davoody_tube.h", "davoody_transfer.h", "davoody_kernels.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

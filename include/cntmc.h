@@ -235,6 +235,54 @@ double  cntmc_multi_time(const cntmc_multi_t* m);
 int  cntmc_multi_init(cntmc_multi_t* m, int64_t c1_pop, int64_t c2_pop, uint64_t seed);
 int  cntmc_multi_step(cntmc_multi_t* m, double dt, int64_t nsteps, int64_t* pop_out, int64_t* curr_out);
 
+/* ---- davoody rate table ("rate type":"davoody") -------------------------------------------------------------------------
+ * The reference builds this table in monte_carlo::create_scattering_table (monte_carlo.cpp:24-49: one cnt object per
+ * entry of the JSON's "cnts", cnt::calculate_exciton_dispersion each) and monte_carlo::create_davoody_scatt_table
+ * (monte_carlo.cpp:64-153: exciton_transfer::first_order for every (theta, z shift, axis shift 1, axis shift 2) entry,
+ * 21 x 11 x 11 x 11 = 27 951 placements in the shipped input.json).  Here: the tube physics runs on the host once per
+ * tube, the placement-independent factors once per tube pair, and every table entry is one thread block of one kernel.
+ * Errors of this section are reported by cntmc_davoody_last_error() (they have no cntmc_t). */
+typedef struct cntmc_tube     cntmc_tube_t;
+typedef struct cntmc_transfer cntmc_transfer_t;
+const char* cntmc_davoody_last_error(void);
+
+/* cnt::cnt(json, dir) + cnt::calculate_exciton_dispersion  exciton_transfer/cnt.h:159-193, cnt.cpp:1056-1081: chirality
+ * (n, m), length in cnt unit cells ("length": [L, "cnt unit cells"]).  Host only; writes no files.  NULL on failure. */
+cntmc_tube_t* cntmc_tube_create(int n, int m, int length_cells);
+void          cntmc_tube_destroy(cntmc_tube_t* t);
+/* ints = {n, m, cells, Nu, M, Q, nk (K2-extended), sites = Nu*cells}; reals = {cnt::radius() cnt.h:261, length_in_meter()
+ * :318, Au() :346, seconds the build took} */
+int cntmc_tube_info(const cntmc_tube_t* t, int32_t ints[8], double reals[4]);
+/* cnt::A1() / A2_singlet() / A2_triplet()  cnt.h:273-309: which = 0 / 1 / 2.  dims = {nk_cm, n_principal, nk_c,
+ * ik_cm_range[0]}; energy is exciton_struct::energy(ik_cm_idx, n), row-major [nk_cm][n_principal], joules */
+int cntmc_tube_exciton_dims(const cntmc_tube_t* t, int which, int32_t dims[4]);
+int cntmc_tube_exciton_energy(const cntmc_tube_t* t, int which, double* energy);
+
+/* exciton_transfer::exciton_transfer(cnt1, cnt2)  exciton_transfer.h:37-48 (which fixes 300 K and 4 meV; here they are
+ * arguments, broadening in joules): relevant states, matched pairs, Q of every pair, site phases; uploads them to
+ * `device` (< 0: the current one).  Both tubes must outlive the transfer.  NULL on failure (no CUDA device included). */
+cntmc_transfer_t* cntmc_transfer_create(const cntmc_tube_t* donor, const cntmc_tube_t* acceptor, double temperature_kelvin,
+                                        double broadening_joule, int device);
+void              cntmc_transfer_destroy(cntmc_transfer_t* x);
+/* ints = {donor states, acceptor states, matched pairs, distinct donor K_cm, distinct acceptor K_cm, K_cm per pass,
+ * threads per block, shared memory bytes}; reals = {temperature, broadening, last kernel ms, launches so far} */
+int cntmc_transfer_info(const cntmc_transfer_t* x, int32_t ints[8], double reals[4]);
+/* per matched pair, in the reference's pair order: Q (calculate_Q, exciton_transfer.cpp:274-304) as re,im; the thermal
+ * prefactor (2 pi / hbar) exp(-E_i/kT)/Z and the lorentzian of first_order's sum (:431).  Any pointer may be NULL. */
+int cntmc_transfer_pair_factors(const cntmc_transfer_t* x, double* q_re_im, double* boltzmann, double* lorentzian);
+/* exciton_transfer::first_order(z_shift, {axis_shift_1, axis_shift_2}, theta)  exciton_transfer.cpp:395-441 for n
+ * placements at once (theta in radians, lengths in metres); rate[n] in 1/s */
+int cntmc_transfer_first_order(cntmc_transfer_t* x, int64_t n, const double* z_shift, const double* axis_shift_1,
+                               const double* axis_shift_2, const double* theta, double* rate);
+/* the loop nest of monte_carlo::create_davoody_scatt_table  monte_carlo.cpp:114-137 over the four axes; rates is
+ * [theta][z][a1][a2] like cntmc_set_rate_table's */
+int cntmc_transfer_table(cntmc_transfer_t* x, const int32_t dims[4], const double* theta, const double* z_shift,
+                         const double* axis_shift_1, const double* axis_shift_2, double* rates);
+/* the same, installed into a simulation as its scattering table (create_davoody_scatt_table's return value,
+ * monte_carlo.cpp:139); must precede cntmc_kubo_init / cntmc_init like cntmc_set_rate_table */
+int cntmc_create_davoody_table(cntmc_t* h, cntmc_transfer_t* x, const int32_t dims[4], const double* theta,
+                               const double* z_shift, const double* axis_shift_1, const double* axis_shift_2);
+
 #ifdef __cplusplus
 }
 #endif
