@@ -51,8 +51,11 @@ int main(int argc, char* argv[]) {
     const cntmc::json::Value j = cntmc::json::parse(text.str());
     if (!j.contains("exciton monte carlo"))
       throw std::invalid_argument("json input file does not contain \"exciton monte carlo\"");
+    // if the exciton transfer type is davoody the tubes' description goes with the block (reference main.cpp:51-54)
+    cntmc::json::Value json_mc = j.at("exciton monte carlo");
+    if (json_mc.at("rate type").as_string() == "davoody") json_mc.obj.push_back({"cnts", j.at("cnts")});
     std::ostringstream block;
-    cntmc::json::dump(j.at("exciton monte carlo"), block);
+    cntmc::json::dump(json_mc, block);
 
     mc::monte_carlo sim(block.str(), (int)n_gpus);
     sim.set_seed(seed);

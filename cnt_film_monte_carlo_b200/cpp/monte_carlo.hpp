@@ -136,6 +136,8 @@ class monte_carlo {
       ok(cntmc_load_mesh(_h, _input_directory.string().c_str()));
       ok(cntmc_kubo_init(_h));
     }
+    // create_davoody_scatt_table leaves its table in the output directory (monte_carlo.cpp:150); the closed-form ones do not
+    if (_json_prop.at("rate type").as_string() == "davoody") save_scat_table();
     ok(cntmc_get_domain(_h, _domain));
     int64_t n = 0;
     ok(cntmc_num_sites(_h, &n));
@@ -196,6 +198,7 @@ class monte_carlo {
       ok(cntmc_load_mesh(_h, _input_directory.string().c_str()));
       ok(cntmc_init(_h, c1_pop, c2_pop, _seed, 0));
     }
+    if (_json_prop.at("rate type").as_string() == "davoody") save_scat_table();  // monte_carlo.cpp:150
     _n_seg = (unsigned)cntmc_number_of_segments(_h);
     _area.resize(_n_seg);
     ok(cntmc_get_area(_h, _area.data()));

@@ -323,6 +323,35 @@ void check_flags(cntmc_t* h) {
   if (flags[FLAG_STUCK]) throw StateError("an exciton exceeded the chain-walk guard (coincident chain sites?)");
 }
 
+// monte_carlo::create_scattering_table, "davoody" branch (monte_carlo.cpp:32-49): tube physics for the input's tubes, then
+// the table of transfers from the first tube to itself, on this handle's GPU (cntmc_davoody.cu)
+void davoody_table(cntmc_t* h) {
+  struct TubeHandle {
+    cntmc_tube_t* t = nullptr;
+    ~TubeHandle() { cntmc_tube_destroy(t); }
+  };
+  struct TransferHandle {
+    cntmc_transfer_t* x = nullptr;
+    ~TransferHandle() { cntmc_transfer_destroy(x); }
+  };
+  std::vector<std::unique_ptr<TubeHandle>> tubes;
+  for (const auto& spec : h->prm.tubes) {  // the reference solves every listed tube, then uses the first
+    tubes.emplace_back(new TubeHandle);
+    tubes.back()->t = cntmc_tube_create(spec[0], spec[1], spec[2]);
+    if (!tubes.back()->t) throw std::invalid_argument(std::string("\"cnts\": ") + cntmc_davoody_last_error());
+  }
+  HostTable      t = make_table_axes(h->prm);
+  TransferHandle x;
+  // exciton_transfer(cnt1, cnt2) fixes 300 K and 4 meV (exciton_transfer.h:41-42)
+  x.x = cntmc_transfer_create(tubes[0]->t, tubes[0]->t, 300, 4.e-3 * (1.6 * std::pow(10, -19.0)), h->device);
+  if (!x.x) throw CudaError(cntmc_davoody_last_error());
+  const int32_t dims[4] = {(int32_t)t.theta.size(), (int32_t)t.z.size(), (int32_t)t.a1.size(), (int32_t)t.a2.size()};
+  t.rates.resize(t.theta.size() * t.z.size() * t.a1.size() * t.a2.size());
+  if (cntmc_transfer_table(x.x, dims, t.theta.data(), t.z.data(), t.a1.data(), t.a2.data(), t.rates.data()) != CNTMC_OK)
+    throw CudaError(cntmc_davoody_last_error());
+  h->table = std::move(t);
+}
+
 // ---- set-up common to kubo_init and init -------------------------------------------------------------------------------
 // monte_carlo.cpp:262-298 / monte_carlo.h:166-186: table, scatterers, trim, domain, buckets, set_max_rate
 void common_init(cntmc_t* h) {
@@ -331,6 +360,7 @@ void common_init(cntmc_t* h) {
     h->mesh = load_mesh(expand_home(h->prm.mesh_dir));
     h->have_mesh = true;
   }
+  if (h->table.empty() && h->prm.rate_type == "davoody" && !h->prm.tubes.empty()) davoody_table(h);
   if (h->table.empty()) h->table = make_rate_table(h->prm);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -870,6 +900,7 @@ int cntmc_create(const char* json_text, cntmc_t** out) {
     const json::Value      doc = json::parse(json_text);
     h->block = mc_block(doc);
     h->prm = parse_params(h->block);
+    if (const json::Value* cnts = doc.find("cnts") ? doc.find("cnts") : h->block.find("cnts")) h->prm.tubes = parse_tubes(*cnts);
     // the kernels divide by the velocity with div_by (hop_core.h), which is exact for every divisor but these
     if (div_by_unsafe(h->prm.velocity))
       throw std::invalid_argument("\"exciton velocity [m/s]\": a value whose binary significand is all ones is not supported");

@@ -92,6 +92,34 @@ std::vector<double> linspace(double start, double end, int64_t n) {
   return x;
 }
 
+std::vector<std::array<int, 3>> parse_tubes(const json::Value& cnts) {
+  if (!cnts.is_object()) throw std::invalid_argument("json: \"cnts\" is not an object");
+  std::vector<std::pair<std::string, std::array<int, 3>>> named;
+  for (const auto& kv : cnts.obj) {
+    if (kv.first == "directory" || kv.first == "comment") continue;  // erased at monte_carlo.cpp:35-37
+    const json::Value& chirality = kv.second.at("chirality");
+    const json::Value& length = kv.second.at("length");
+    if (length.at(1).as_string() != "cnt unit cells")  // message of cnt.h:187
+      throw std::invalid_argument("units other than \"cnt unit cells\" is not implemented yet!!!");
+    named.push_back({kv.first, {(int)chirality.at(0).as_number(), (int)chirality.at(1).as_number(), (int)length.at(0).as_number()}});
+  }
+  std::sort(named.begin(), named.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+  std::vector<std::array<int, 3>> out;
+  for (const auto& kv : named) out.push_back(kv.second);
+  return out;
+}
+
+HostTable make_table_axes(const Params& p) {
+  if (!p.has_table_grids) throw std::invalid_argument("json: the four rate-table grids are required");
+  HostTable t;
+  t.z = linspace(p.zshift[0], p.zshift[1], (int64_t)p.zshift[2]);
+  t.a1 = linspace(p.ashift1[0], p.ashift1[1], (int64_t)p.ashift1[2]);
+  t.a2 = linspace(p.ashift2[0], p.ashift2[1], (int64_t)p.ashift2[2]);
+  t.theta = linspace(p.theta_deg[0], p.theta_deg[1], (int64_t)p.theta_deg[2]);
+  for (double& th : t.theta) th *= (kRefPi / 180);
+  return t;
+}
+
 HostTable make_rate_table(const Params& p) {
   double gamma0;
   if (p.rate_type == "forster") {
@@ -100,19 +128,13 @@ HostTable make_rate_table(const Params& p) {
     gamma0 = 1.e13;
   } else if (p.rate_type == "davoody") {
     throw std::invalid_argument(
-        "rate type \"davoody\" needs a precomputed table: load scat_table.*.dat with cntmc_set_rate_table "
-        "(the exciton_transfer / cnt solver is outside this engine's scope)");
+        "rate type \"davoody\" needs the input's \"cnts\" (the table is then built at initialisation) or a table "
+        "installed with cntmc_set_rate_table / cntmc_load_rate_table / cntmc_create_davoody_table");
   } else {
     // message of monte_carlo.cpp:59
     throw std::invalid_argument("rate type must be one of the following: \"davoody\", \"forster\", \"wong\"");
   }
-  if (!p.has_table_grids) throw std::invalid_argument("json: the four rate-table grids are required");
-  HostTable t;
-  t.z = linspace(p.zshift[0], p.zshift[1], (int64_t)p.zshift[2]);
-  t.a1 = linspace(p.ashift1[0], p.ashift1[1], (int64_t)p.ashift1[2]);
-  t.a2 = linspace(p.ashift2[0], p.ashift2[1], (int64_t)p.ashift2[2]);
-  t.theta = linspace(p.theta_deg[0], p.theta_deg[1], (int64_t)p.theta_deg[2]);
-  for (double& th : t.theta) th *= (kRefPi / 180);
+  HostTable t = make_table_axes(p);
   t.rates.reserve(t.theta.size() * t.z.size() * t.a1.size() * t.a2.size());
   // monte_carlo.cpp:172-193
   for (double th : t.theta)

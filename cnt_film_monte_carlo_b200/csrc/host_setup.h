@@ -27,6 +27,9 @@ struct Params {
   double                max_time = 0;                      // monte_carlo.cpp:304
   int64_t               n_particles = 0;                   // monte_carlo.cpp:309
   bool                  has_table_grids = false;
+  // "cnts" of the input (main.cpp:52-54 copies it into the block when the rate type is davoody): {n, m, length in cnt unit
+  // cells} per tube, in the key order nlohmann::json iterates them (sorted), "directory" and "comment" left out
+  std::vector<std::array<int, 3>> tubes;
 };
 
 // `doc` is either a whole input.json (with an "exciton monte carlo" member, main.cpp:46-49) or that block itself.
@@ -39,8 +42,12 @@ struct HostTable {
   std::vector<double> theta, z, a1, a2, rates;  // rates in [theta][z][a1][a2] C order
   bool                empty() const { return rates.empty(); }
 };
+// the four axes of the table (monte_carlo.cpp:65-75 / 157-167), rates left empty
+HostTable make_table_axes(const Params& p);
 // monte_carlo::create_scattering_table for "forster" (gamma0 = 1e15) and "wong" (1e13)  (monte_carlo.cpp:24-61, 156-200)
 HostTable make_rate_table(const Params& p);
+// the tubes of a "cnts" object (monte_carlo.cpp:33-47, cnt.h:159-193)
+std::vector<std::array<int, 3>> parse_tubes(const json::Value& cnts);
 // scattering_struct::save (scattering_struct.h:56-94): dir/scat_table.{theta,z_shift,axis_shift_1,axis_shift_2,rates}.dat.
 // Same files and layout (axes one value per line; rates.dat = "sizes:" header, the four sizes, a blank line, then the
 // rates theta-major); values are written with 17 significant digits so that a saved table loads back bit for bit

@@ -32,6 +32,8 @@ def _load():
         L.f1_cnt_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.f1_first_order.argtypes = [C.c_int, C.c_int] + [C.c_double] * 4
         L.f1_first_order.restype = C.c_double
+        L.f1_first_order_at.argtypes = [C.c_int, C.c_int] + [C.c_double] * 6
+        L.f1_first_order_at.restype = C.c_double
         L.f1_table.argtypes = [C.c_int, C.c_int] + [C.c_int, C.c_void_p] * 4 + [C.c_void_p]
         for name in ("f1_radius", "f1_length_in_meter", "f1_Au"):
             getattr(L, name).restype = C.c_double
@@ -87,6 +89,20 @@ def first_order(donor: RefTube, acceptor: RefTube, z_shift: float, axis_shift_1:
     L = _load()
     with _quiet():
         r = L.f1_first_order(donor.id, acceptor.id, z_shift, axis_shift_1, axis_shift_2, theta)
+    return float(r)
+
+
+def first_order_at(donor: RefTube, acceptor: RefTube, temperature: float, broadening_mev: float, z_shift: float, axis_shift_1: float,
+                   axis_shift_2: float, theta: float) -> float:
+    """first_order at a temperature [K] and broadening [meV]: the two-tube constructor fixes 300 K and 4 meV, everything else
+    goes through the reference's JSON constructor (which cannot tell two tubes of one chirality apart)."""
+    if temperature == 300.0 and broadening_mev == 4.0:
+        return first_order(donor, acceptor, z_shift, axis_shift_1, axis_shift_2, theta)
+    L = _load()
+    with _quiet():
+        r = L.f1_first_order_at(donor.id, acceptor.id, temperature, broadening_mev, z_shift, axis_shift_1, axis_shift_2, theta)
+    if r < 0:
+        raise RuntimeError(L.f1_last_error().decode())
     return float(r)
 
 

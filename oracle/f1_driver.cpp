@@ -88,6 +88,33 @@ double f1_first_order(int donor, int acceptor, double z_shift, double axis_shift
   }
 }
 
+// the same through the reference's other constructor (exciton_transfer.h:51-98), which takes temperature [Kelvin] and
+// broadening [meV] from JSON and finds its tubes by name in a vector; the copies made for that vector keep pointing at
+// the originals' band data, which stay alive in g_cnts
+double f1_first_order_at(int donor, int acceptor, double temperature, double broadening_mev, double z_shift, double axis_shift_1,
+                         double axis_shift_2, double theta) {
+  try {
+    if (acceptor != donor && g_cnts[donor]->name() == g_cnts[acceptor]->name())
+      throw std::invalid_argument("the reference finds its tubes by name: two different tubes of one chirality cannot be told apart");
+    std::vector<cnt> pool;
+    pool.reserve(2);
+    pool.emplace_back(*g_cnts[donor]);
+    if (acceptor != donor) pool.emplace_back(*g_cnts[acceptor]);
+    nlohmann::json j;
+    j["cnt 1"] = g_cnts[donor]->name();
+    j["cnt 2"] = g_cnts[acceptor]->name();
+    j["temperature"] = {temperature, "Kelvin"};
+    j["broadening factor"] = {broadening_mev, "meV"};
+    j["keep old results"] = false;
+    const char* home = getenv("HOME");
+    exciton_transfer ex_transfer(j, pool, std::string(home ? home : ".") + "/exciton_transfer_json");
+    return ex_transfer.first_order(z_shift, {axis_shift_1, axis_shift_2}, theta, false);
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1.0;
+  }
+}
+
 // rate[((i_th * nz + i_z) * n1 + i_1) * n2 + i_2], the loop nest of monte_carlo.cpp:114-137
 int f1_table(int donor, int acceptor, int nth, const double* theta, int nz, const double* z, int n1, const double* a1, int n2,
              const double* a2, double* rate) {

@@ -1,0 +1,152 @@
+"""The davoody rate table on the GPU (csrc/davoody_kernels.cuh through the C ABI) against the reference's own
+exciton_transfer::first_order: committed vectors (tests/golden/davoody.npz) and, where oracle/_ref/libf1.so travelled with
+the snapshot, the reference code live.
+
+Tolerance.  Site positions, distances, Q and the thermal factors are formed with the reference's operations in the
+reference's order; what differs is the order in which the N_d x N_a terms of each Coulomb sum J are added (blocked on the
+GPU, one sequential loop in the reference).  Rates therefore agree to a few 1e-14 relative in practice; the tests allow
+RTOL = 1e-11."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import davoody_case as dc
+from cnt_film_monte_carlo_b200 import build as B
+from cnt_film_monte_carlo_b200 import davoody as dv
+from cnt_film_monte_carlo_b200 import film
+from cnt_film_monte_carlo_b200.engine import Engine
+from conftest import base_mc
+from oracle import f1
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-11
+PI = 3.141592
+
+_tubes = {}
+
+
+def tube(spec):
+    if spec not in _tubes:
+        _tubes[spec] = dv.Tube(*spec)
+    return _tubes[spec]
+
+
+def close(ours, ref):
+    return np.all(np.abs(ours - ref) <= RTOL * np.abs(ref))
+
+
+def test_first_order_matches_the_reference_vectors():
+    """Every case of the fixture: one, two K_cm passes of 4 / 8 / 16, tubes of unequal length, another broadening and
+    temperature, and a pair of tubes without energy-matched states (all zeros)."""
+    z = dc.load()
+    seen_chunks = set()
+    for c in dc.cases(z):
+        x = dv.Transfer(tube(c["donor"]), tube(c["acceptor"]), c["temperature"], c["broadening_mev"] * 1.e-3 * dv.EV)
+        p = c["placements"]
+        ours = x.first_order(p[:, 0], p[:, 1], p[:, 2], p[:, 3])
+        assert close(ours, c["rates"]), (c["donor"], c["acceptor"], ours, c["rates"])
+        info = x.info()
+        if info["pairs"]:
+            seen_chunks.add((info["kcm_per_pass"], -(-info["donor_kcm"] // info["kcm_per_pass"])))
+        else:
+            assert not ours.any()
+    assert {(4, 1), (8, 1), (16, 1), (16, 2)} <= seen_chunks
+
+
+@pytest.mark.skipif(not f1.available(), reason="oracle/_ref/libf1.so did not travel")
+def test_first_order_matches_the_reference_code_live():
+    rng = np.random.default_rng(5)
+    for d, a in [((4, 2, 10), (4, 2, 10)), ((7, 5, 2), (7, 5, 2)), ((8, 0, 30), (8, 0, 30)), ((5, 3, 6), (5, 3, 9))]:
+        x = dv.Transfer(tube(d), tube(a))
+        rd, ra = f1.RefTube(*d), f1.RefTube(*a)
+        n = 5
+        z, s1, s2, th = rng.uniform(1.5e-9, 10e-9, n), rng.uniform(-10e-9, 10e-9, n), rng.uniform(-10e-9, 10e-9, n), rng.uniform(0, PI, n)
+        ours = x.first_order(z, s1, s2, th)
+        ref = np.array([f1.first_order(rd, ra, *g) for g in zip(z, s1, s2, th)])
+        assert close(ours, ref), (d, a, ours, ref)
+
+
+def test_input_json_table_full_size():
+    """The shipped input.json's table (21 x 11 x 11 x 11 = 27 951 placements of a (4,2) x 10-cell tube against itself):
+    repeatable bit for bit, equal to entry-by-entry calls, invariant under a common shift of both tubes along parallel axes
+    and under exchanging the roles of the two identical tubes, and equal to the reference on a sample of entries."""
+    cfg = {"cnts": {"directory": "~/x", "comment": "c", "1": {"chirality": [4, 2], "length": [10, "cnt unit cells"]}},
+           "exciton monte carlo": base_mc(**{"rate type": "davoody"})}
+    theta, z, a1, a2, rates, x = dv.table_from_json(cfg)
+    assert rates.shape == (21, 11, 11, 11) and np.all(rates > 0) and np.all(np.isfinite(rates))
+    assert np.array_equal(rates, x.table(theta, z, a1, a2))
+    # a table entry is first_order at that placement
+    idx = [(0, 0, 0, 0), (20, 10, 10, 10), (7, 3, 9, 1), (10, 0, 5, 5)]
+    single = np.array([x.first_order(z[k], a1[p], a2[q], theta[i]).item() for i, k, p, q in idx])
+    assert np.array_equal(single, np.array([rates[i] for i in idx]))
+    # theta = 0: only the difference of the two axis shifts matters (both tubes slide together)
+    t0 = rates[0]
+    for k in range(0, 11, 5):
+        for s in range(-5, 6):
+            diag = np.array([t0[k, p, p + s] for p in range(max(0, -s), min(11, 11 - s))])
+            assert np.all(np.abs(diag - diag[0]) <= 1e-9 * diag[0])
+    # identical tubes, parallel axes: swapping donor and acceptor mirrors the axis shifts
+    assert np.allclose(t0, np.transpose(t0, (0, 2, 1)), rtol=1e-9, atol=0)
+    # nearest placement transfers fastest, and the rate falls with distance
+    assert rates.max() == rates[:, 0].max() and np.all(rates[:, 0].mean(axis=(1, 2)) > rates[:, -1].mean(axis=(1, 2)))
+    if f1.available():
+        r = f1.RefTube(4, 2, 10)
+        ref = f1.table(r, r, theta[[0, 9, 20]], z[[0, 6]], a1[[0, 5]], a2[[3, 10]])
+        assert close(rates[np.ix_([0, 9, 20], [0, 6], [0, 5], [3, 10])], ref)
+
+
+def test_engine_builds_its_davoody_table_at_init(golden_small):
+    """"rate type": "davoody" with the input's "cnts": kubo_init builds the table (monte_carlo.cpp:32-49) and hops on it."""
+    g = golden_small
+    mc = dict(g.mc)
+    mc.update({"rate type": "davoody", "theta [degrees]": [0, 180, 5], "zshift [m]": [1.5e-9, 10e-9, 4],
+               "axis shift 1 [m]": [-10e-9, 10e-9, 3], "axis shift 2 [m]": [-10e-9, 10e-9, 3]})
+    cnts = {"directory": "~/x", "comment": "c", "2": {"chirality": [5, 3], "length": [2, "cnt unit cells"]},
+            "1": {"chirality": [4, 2], "length": [6, "cnt unit cells"]}}
+    e = Engine({"cnts": cnts, "exciton monte carlo": mc})
+    e.set_mesh(g.pos_nm, g.orient)
+    e.kubo_init()
+    theta, z, a1, a2, rates = e.rate_table()
+    x = dv.Transfer(tube((4, 2, 6)), tube((4, 2, 6)))      # the first tube in key order, to itself
+    axes = dv.table_axes(mc)
+    for got, want in zip((theta, z, a1, a2), axes):
+        assert np.array_equal(got, want)
+    assert np.array_equal(rates, x.table(*axes))
+    e.kubo_create_particles(g.P, seed=g.seed)
+    msd = e.kubo_step(g.dt, 50)
+    assert e.hops() > 0 and np.all(np.isfinite(msd))
+    # the same table installed by hand gives the same run
+    e2 = Engine(mc)
+    e2.set_mesh(g.pos_nm, g.orient)
+    x.install(e2, *axes)
+    e2.kubo_init()
+    e2.kubo_create_particles(g.P, seed=g.seed)
+    assert np.array_equal(msd, e2.kubo_step(g.dt, 50)) and e2.hops() == e.hops()
+
+
+def test_driver_runs_a_davoody_input(tmp_path, golden_small):
+    """cntmc_main on an input.json whose rate type is davoody (main.cpp:51-54 hands "cnts" to the block)."""
+    g = golden_small
+    mesh = str(tmp_path / "mesh")
+    film.write_mesh(mesh, g.pos_nm, g.orient)
+    mc = dict(g.mc)
+    mc.update({"rate type": "davoody", "theta [degrees]": [0, 180, 3], "zshift [m]": [1.5e-9, 10e-9, 3],
+               "axis shift 1 [m]": [-10e-9, 10e-9, 3], "axis shift 2 [m]": [-10e-9, 10e-9, 3], "mesh input directory": mesh,
+               "output directory": str(tmp_path / "out"), "keep old results": False,
+               "maximum time for kubo simulation [seconds]": 20 * float(mc["monte carlo time step"])})
+    path = str(tmp_path / "input.json")
+    with open(path, "w") as f:
+        json.dump({"cnts": {"directory": "~/x", "1": {"chirality": [4, 2], "length": [4, "cnt unit cells"]}}, "exciton monte carlo": mc}, f)
+    B.build_driver()
+    r = subprocess.run([B.DRIVER, path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = str(tmp_path / "out")
+    rates = open(os.path.join(out, "scat_table.rates.dat")).read().split()
+    assert rates[0] == "sizes:" and [int(v) for v in rates[1:5]] == [3, 3, 3, 3]
+    x = dv.Transfer(tube((4, 2, 4)), tube((4, 2, 4)))
+    want = x.table(*dv.table_axes(mc))
+    got = np.array([float(v) for v in rates[5:]]).reshape(3, 3, 3, 3)
+    assert np.array_equal(got, want)
