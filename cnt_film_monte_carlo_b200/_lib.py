@@ -104,6 +104,8 @@ SIGNATURES = {
     "cntmc_transfer_first_order": (C.c_int, [V, I64, V, V, V, V, V]),
     "cntmc_transfer_table": (C.c_int, [V, V, V, V, V, V, V]),
     "cntmc_create_davoody_table": (C.c_int, [V, V, V, V, V, V, V]),
+    "cntmc_fp64_peak": (C.c_int, [C.c_int, V]),
+    "cntmc_hermitian_eig": (C.c_int, [C.c_int, V, V, V]),
 }
 
 _lib = None

@@ -187,6 +187,10 @@ struct cntmc_handle {
   int32_t                    trace_cap = 0;
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // overlap mode of the trap kernel: its own stream, and the events that order it against the handle's stream
+  cudaStream_t     trap_stream = nullptr;
+  cudaEvent_t      ev_fork = nullptr, ev_join = nullptr;
+  DevBuf<uint32_t> d_overlap_sync;
   double      last_ms = 0;
   int64_t     last_launches = 0;
 
@@ -201,6 +205,10 @@ struct cntmc_handle {
                               // parity-green but slower on every workload measured, profiles/round2_trap_solver.txt)
   int64_t opt_deep_blocks = 4;  // blocks per SM of the trap solver's launch
   int64_t opt_deep_group = 8;   // lanes per exciton in the trap solver (8: window walk; 1: the generic loop over trapped excitons only)
+  int64_t opt_trap_burst = 1;   // events per lane and warp iteration of the trap-lanes kernel (deep_group = 1; see hop_loop)
+  int64_t opt_deep_overlap = 0;  // deep_group = 1 only: the trap kernel runs beside the lane kernel of the same launch and takes
+                                 // the deferred excitons while they arrive (see hop_loop)
+  int64_t opt_overlap_trap_blocks = 1;  // blocks per SM of the trap kernel in overlap mode; the lane kernel takes the rest of five
   int64_t opt_deep_rounds = 2;  // 2: the trap solver hands excitons that left their trap back to the lanes once per launch
   int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
   int64_t opt_stage_mb = 0;  // cap on the (step, exciton) staging buffer in MiB; shortens the launches if needed.
@@ -229,6 +237,9 @@ struct cntmc_handle {
   ~cntmc_handle() {
     slices.clear();
     if (ev0) cudaEventDestroy(ev0);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (trap_stream) cudaStreamDestroy(trap_stream);
     if (ev1) cudaEventDestroy(ev1);
     if (is_slice && stream) cudaStreamDestroy(stream);
   }
@@ -752,6 +763,7 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     a.n_sites = h->sites.N;
     a.hot_blocks = (int32_t)((int64_t)grid * h->opt_hot_pct / 100);
     a.top_entries = (int32_t)h->opt_top_entries;
+    a.burst = 1;
     a.deep_thr = deep_thr;
     a.deep_rate = a.deep_thr / dt;
     a.P = h->P;
@@ -774,8 +786,44 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
     // Round 1: the lanes serve classes 0-3 and defer what lands in a deep trap; the trap solver serves class 4 and the
     // deferred, and hands back what ends a time step outside a trap.  Round 2: the lanes finish the returned (deferring
     // again), the trap solver finishes whatever is left and keeps it.  Kernels whose lists are empty leave at once.
-    const int rounds = deep ? (int)std::max<int64_t>(1, std::min<int64_t>(2, h->opt_deep_rounds)) : 1;
-    for (int round = 1; round <= rounds; ++round) {
+    const bool overlap = deep && h->opt_deep_overlap != 0 && h->opt_deep_group == 1;
+    const int  rounds = (deep && !overlap) ? (int)std::max<int64_t>(1, std::min<int64_t>(2, h->opt_deep_rounds)) : 1;
+    if (overlap) {
+      // One launch = the lane kernel on the handle's stream and the trap kernel on a stream of its own, side by side.  The
+      // lane kernel never waits for the trap kernel, so the pair cannot deadlock whatever order the blocks are placed in; the
+      // trap kernel leaves when the lane kernel has finished and the deferred list is empty.
+      if (!h->trap_stream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->trap_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+      }
+      h->d_overlap_sync.alloc(32);
+      CUDA_CHECK(cudaMemsetAsync(h->d_overlap_sync.p, 0, 32 * sizeof(uint32_t), st));
+      CUDA_CHECK(cudaMemsetAsync(h->d_hand_list[0].p, 0, (size_t)h->P * sizeof(uint32_t), st));  // empty slots read 0
+      const int64_t  tb = std::max<int64_t>(1, std::min<int64_t>(4, h->opt_overlap_trap_blocks));
+      const unsigned lane_grid = (unsigned)std::min<int64_t>(want, std::max<int64_t>(1, (int64_t)h->sm_count * (5 - tb)));
+      const unsigned trap_grid = (unsigned)((int64_t)h->sm_count * tb);
+      a.yield_on = 0;
+      a.overlap = 1;
+      a.lane_grid = (int32_t)lane_grid;
+      a.sync = h->d_overlap_sync.p;
+      a.hot_blocks = (int32_t)((int64_t)lane_grid * h->opt_hot_pct / 100);
+      CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
+      CUDA_CHECK(cudaStreamWaitEvent(h->trap_stream, h->ev_fork, 0));
+      launch_kubo<PhiloxDraws>(h, a, lane_grid, st, true);
+      CUDA_CHECK(cudaGetLastError());
+      KuboArgs b = a;
+      b.burst = (int32_t)h->opt_trap_burst;
+      if (h->trace_cap > 0 || h->opt_stats)
+        trap_lanes_kernel<true><<<trap_grid, 128, 0, h->trap_stream>>>(b);
+      else
+        trap_lanes_kernel<false><<<trap_grid, 128, 0, h->trap_stream>>>(b);
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaEventRecord(h->ev_join, h->trap_stream));
+      CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join, 0));
+      h->last_launches += 2;
+    }
+    for (int round = 1; round <= rounds && !overlap; ++round) {
       a.round = round;
       a.yield_on = (deep && round < rounds) ? 1 : 0;
       if (round == 2) {  // the deferred list starts again (the trap solver has emptied it)
@@ -801,10 +849,12 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
         const bool instr = h->trace_cap > 0 || h->opt_stats;
         if (h->opt_deep_group == 1) {
           const unsigned lgrid = (unsigned)((int64_t)h->sm_count * 5);
+          KuboArgs       b = a;
+          b.burst = (int32_t)h->opt_trap_burst;
           if (instr)
-            trap_lanes_kernel<true><<<lgrid, 128, 0, st>>>(a);
+            trap_lanes_kernel<true><<<lgrid, 128, 0, st>>>(b);
           else
-            trap_lanes_kernel<false><<<lgrid, 128, 0, st>>>(a);
+            trap_lanes_kernel<false><<<lgrid, 128, 0, st>>>(b);
         } else if (instr)
           deep_kernel<true><<<dgrid, 128, 0, st>>>(a);
         else
@@ -1118,7 +1168,8 @@ int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P,
         s->T = h->T;
         s->opt_chunk = h->opt_chunk; s->opt_hot_pct = h->opt_hot_pct; s->opt_occupancy = h->opt_occupancy;
         s->opt_top_entries = h->opt_top_entries; s->opt_deep_thr = h->opt_deep_thr; s->opt_deep_blocks = h->opt_deep_blocks;
-        s->opt_deep_rounds = h->opt_deep_rounds;
+        s->opt_deep_rounds = h->opt_deep_rounds; s->opt_trap_burst = h->opt_trap_burst;
+        s->opt_deep_overlap = h->opt_deep_overlap; s->opt_overlap_trap_blocks = h->opt_overlap_trap_blocks;
         if (s->opt_stage_mb <= 0 && h->opt_stage_mb > 0) s->opt_stage_mb = std::max<int64_t>(64, h->opt_stage_mb / K);
         s->grid_share = std::max<int64_t>(1, std::min<int64_t>(K, h->opt_slice_share > 0 ? h->opt_slice_share : K));
         s->replay = h->replay;
@@ -1701,6 +1752,15 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
     } else if (k == "deep_group") {
       require(value == 1 || value == 8, "deep_group must be 1 or 8");
       h->opt_deep_group = value;
+    } else if (k == "trap_burst") {
+      require(value >= 1 && value <= 4096, "trap_burst must be in [1, 4096]");
+      h->opt_trap_burst = value;
+    } else if (k == "deep_overlap") {
+      require(value == 0 || value == 1, "deep_overlap must be 0 or 1");
+      h->opt_deep_overlap = value;
+    } else if (k == "overlap_trap_blocks") {
+      require(value >= 1 && value <= 4, "overlap_trap_blocks must be in [1, 4]");
+      h->opt_overlap_trap_blocks = value;
     } else if (k == "deep_rounds") {
       require(value >= 1 && value <= 2, "deep_rounds must be 1 or 2");
       h->opt_deep_rounds = value;
@@ -1741,6 +1801,9 @@ int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   if (k == "deep_thr") return h->opt_deep_thr;
   if (k == "deep_blocks") return h->opt_deep_blocks;
   if (k == "deep_rounds") return h->opt_deep_rounds;
+  if (k == "deep_overlap") return h->opt_deep_overlap;
+  if (k == "overlap_trap_blocks") return h->opt_overlap_trap_blocks;
+  if (k == "trap_burst") return h->opt_trap_burst;
   if (k == "deep_group") return h->opt_deep_group;
   if (k == "host_slices") return h->opt_host_slices;
   if (k == "guard_ppb") return h->opt_guard_ppb;

@@ -89,7 +89,65 @@ struct cntmc_transfer {
   long long                 launches = 0;
 };
 
+// Measured FP64 pipe peak of the device, the denominator of the table kernel's roofline: 8 independent fused multiply-add
+// chains per thread, enough resident warps to fill every SM, no memory traffic.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0 - 1e-9, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double v = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (v == 12345.678) out[0] = v;  // keeps the chains alive
+}
+
+#include "herm_eig.h"
 extern "C" {
+
+int cntmc_hermitian_eig(int n, const double* a_re_im, double* w, double* v_re_im) {
+  return guarded([&] {
+    require(n > 0 && a_re_im && w && v_re_im, "bad argument");
+    std::vector<std::complex<double>> A((size_t)n * n), V((size_t)n * n);
+    for (size_t k = 0; k < A.size(); k++) A[k] = std::complex<double>(a_re_im[2 * k], a_re_im[2 * k + 1]);
+    const int sweeps = cntmc::hermitian_eig(n, A.data(), w, V.data());
+    require(sweeps >= 0, "the Jacobi sweeps did not converge");
+    for (size_t k = 0; k < V.size(); k++) {
+      v_re_im[2 * k] = V[k].real();
+      v_re_im[2 * k + 1] = V[k].imag();
+    }
+  });
+}
+
+int cntmc_fp64_peak(int device, double* tflops) {
+  return guarded([&] {
+    require(tflops != nullptr, "null argument");
+    DV_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    DV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    Dev<double> out;
+    out.reserve(1);
+    const int   iters = 1 << 15, blocks = sms * 8;
+    cudaEvent_t e0, e1;
+    DV_CUDA(cudaEventCreate(&e0));
+    DV_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {  // the first pass warms up
+      DV_CUDA(cudaEventRecord(e0, 0));
+      fp64_peak_kernel<<<blocks, 256>>>(out.p, iters, 1.0 + rep);
+      DV_CUDA(cudaEventRecord(e1, 0));
+      DV_CUDA(cudaGetLastError());
+      DV_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      DV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double t = 2.0 * 8 * (double)iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+      if (rep > 0 && t > best) best = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+  });
+}
 
 const char* cntmc_davoody_last_error(void) { return g_error.c_str(); }
 
@@ -158,9 +216,21 @@ cntmc_transfer_t* cntmc_transfer_create(const cntmc_tube_t* donor, const cntmc_t
     const int       Nd = X.donor.n_sites(), Na = X.acceptor.n_sites(), Kd = int(X.d_kcm.size()), Ka = int(X.a_kcm.size());
     h->chunk = Kd <= 4 ? 4 : (Kd <= 8 ? 8 : 16);
     h->Kd_pad = (Kd + h->chunk - 1) / h->chunk * h->chunk;
-    // threads = acceptor sites per pass, balanced over the passes (280 sites: 2 passes of 160 rather than 256 + 24)
-    const int passes = (Na + 255) / 256;
-    h->threads = std::min(256, std::max(32, ((Na + passes - 1) / passes + 31) / 32 * 32));
+    // threads = acceptor sites per pass: the number of passes (of at most 320 threads) that leaves the fewest idle threads
+    // (280 sites: one pass of 288, not 256 + 24 and not 2 x 160; every pass re-stages the donor tiles)
+    int best_passes = 1, best_threads = 0;
+    long best_slots = -1;
+    for (int passes = (Na + 319) / 320; passes <= (Na + 319) / 320 + 3; passes++) {
+      const int  t = std::max(32, ((Na + passes - 1) / passes + 31) / 32 * 32);
+      const long slots = (long)t * passes;
+      if (t <= 320 && (best_slots < 0 || slots < best_slots)) {
+        best_slots = slots;
+        best_passes = passes;
+        best_threads = t;
+      }
+    }
+    (void)best_passes;
+    h->threads = best_threads;
     h->smem = placement_smem_bytes(h->chunk, h->threads, h->Kd_pad, Ka);
     require(h->smem <= 200 * 1024, "too many distinct K_cm among the matched states for one thread block's shared memory");
     h->d_x.put(X.d_sites.x);

@@ -47,7 +47,7 @@ inline size_t placement_smem_bytes(int KC, int threads, int Kd_pad, int Ka) {
 
 // KC = donor K_cm values carried in registers per pass over the distance matrix
 template <int KC>
-__global__ void __launch_bounds__(256) placement_rate_kernel(const PlacementArgs A) {
+__global__ void __launch_bounds__(320) placement_rate_kernel(const PlacementArgs A) {
   extern __shared__ double2 smem2[];
   const int T = blockDim.x, tid = threadIdx.x;
   double2*  Js = smem2;                            // [Kd_pad][Ka]

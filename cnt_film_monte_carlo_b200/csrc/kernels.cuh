@@ -52,6 +52,47 @@ __device__ __forceinline__ void load_lane(Lane& L, const ExcitonArrays& S, const
   L.stuck = false;
   attach_site(L, T);
 }
+// Loads that are served by L2 and never by a (possibly stale) L1 line: for state another kernel wrote while this one was
+// already running (overlap mode of the trap kernel, see hop_loop).  LDG.E.STRONG.GPU; no fence, no L1 invalidation.
+__device__ __forceinline__ double ld_strong(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_strong(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int32_t ld_strong(const int32_t* p) { return (int32_t)ld_strong(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ uint32_t ld_strong(const uint8_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {  // MEMBAR.ALL.GPU + STG.STRONG: everything this thread stored before is visible first
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void load_lane_strong(Lane& L, const ExcitonArrays& S, const Tables& T, int64_t e) {
+  L.px = ld_strong(S.px + e);
+  L.py = ld_strong(S.py + e);
+  L.pz = ld_strong(S.pz + e);
+  L.dx = ld_strong(S.dx + e);
+  L.dy = ld_strong(S.dy + e);
+  L.dz = ld_strong(S.dz + e);
+  L.ff = ld_strong(S.ff + e);
+  L.site = ld_strong(S.site + e);
+  L.heading_right = ld_strong(S.heading + e) != 0;
+  L.ndraw = ld_strong(S.ndraw + e);
+  L.nevent = 0;
+  L.stuck = false;
+  attach_site(L, T);
+}
 __device__ __forceinline__ void store_lane(const Lane& L, const ExcitonArrays& S, int64_t e) {  // needs L.pos_valid
   __stcs(S.px + e, L.px);
   __stcs(S.py + e, L.py);
@@ -158,14 +199,23 @@ __device__ __forceinline__ void file_excitons(const ClassLists& q, bool mine, in
   }
 }
 // hand excitons over to the other kernel: which = 0 lanes -> trap solver (deferred), 1 trap solver -> lanes (returned)
-__device__ __forceinline__ void hand_over(const ClassLists& q, int which, bool mine, uint32_t e, int lane, unsigned lt_mask) {
+// publish: the receiver is running already (overlap mode) and waits for its slot of the list to become non-zero; the entry is
+// e + 1, stored with release semantics so that the exciton's state and cursor, stored by this thread before, are visible first
+__device__ __forceinline__ void hand_over(const ClassLists& q, int which, bool mine, uint32_t e, int lane, unsigned lt_mask,
+                                          bool publish = false) {
   const unsigned m = __ballot_sync(0xffffffffu, mine);
   if (m) {
     uint32_t  base = 0;
     const int leader = __ffs(m) - 1;
     if (lane == leader) base = atomicAdd(q.hand_to + which, (uint32_t)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (mine) q.hand_list[which][base + __popc(m & lt_mask)] = e;
+    if (mine) {
+      uint32_t* slot = q.hand_list[which] + (base + __popc(m & lt_mask));
+      if (publish)
+        st_release(slot, e + 1u);
+      else
+        *slot = e;
+    }
   }
 }
 // hand an exciton to every lane that `want`s one, from the n_serve lists named in `serve`, in that order (call with the
@@ -222,6 +272,10 @@ struct KuboArgs {
   int32_t             hot_blocks;   // blocks [0, hot_blocks) serve the active classes first
   int64_t             n_sites;
   int32_t             top_entries;  // try the three widest entries of a row before searching it
+  int32_t             burst;        // trap-lanes kernel: events a lane may run in a row inside one iteration of its warp (>= 1)
+  int32_t             overlap;      // the lane kernel and the trap kernel of a launch run side by side (see hop_loop)
+  int32_t             lane_grid;    // overlap: blocks of the lane kernel
+  uint32_t*           sync;         // overlap: [0] = blocks of the lane kernel that have finished
   double              deep_thr;     // Gamma*dt from which an exciton belongs to the group solver (inf: never)
   double              deep_rate;    // the same as a rate: deep_thr / dt
   int64_t             P;
@@ -360,7 +414,11 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
 
   auto start = [&]() {
     const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject, nf = L.nfast;
-    load_lane(L, a.S, a.T, (int64_t)e);
+    const bool     fresh = kTrap && G == 1 && a.overlap != 0;  // the state may have been written while this kernel was running
+    if (fresh)
+      load_lane_strong(L, a.S, a.T, (int64_t)e);
+    else
+      load_lane(L, a.S, a.T, (int64_t)e);
     L.ncross = nc;
     L.nprobe = np;
     L.nreinject = nr;
@@ -371,10 +429,17 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
     s_delta[0][tid] = L.dx; s_delta[1][tid] = L.dy; s_delta[2][tid] = L.dz;
     s_old[0][tid] = L.px; s_old[1][tid] = L.py; s_old[2][tid] = L.pz;  // _old_pos = _pos (particle.cpp:59)
     if (kTrap && from == kDeferred) {  // handed over in the middle of a time step
-      step = a.C.step[e];
-      dt_rem = a.C.dt_rem[e];
-      L.nevent = a.C.nevent[e];
-      s_old[0][tid] = a.C.ox[e]; s_old[1][tid] = a.C.oy[e]; s_old[2][tid] = a.C.oz[e];
+      if (fresh) {
+        step = ld_strong(a.C.step + e);
+        dt_rem = ld_strong(a.C.dt_rem + e);
+        L.nevent = ld_strong(a.C.nevent + e);
+        s_old[0][tid] = ld_strong(a.C.ox + e); s_old[1][tid] = ld_strong(a.C.oy + e); s_old[2][tid] = ld_strong(a.C.oz + e);
+      } else {
+        step = a.C.step[e];
+        dt_rem = a.C.dt_rem[e];
+        L.nevent = a.C.nevent[e];
+        s_old[0][tid] = a.C.ox[e]; s_old[1][tid] = a.C.oy[e]; s_old[2][tid] = a.C.oz[e];
+      }
     }
     if (!kTrap && from == kReturned) step = a.C.step[e];  // handed back at a step boundary
     if (kInstr && a.trace_sites) {  // the trace continues where the previous launch stopped
@@ -392,9 +457,31 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
     // round 2 of a launch serves what the other kernel handed over during round 1
     const uint32_t serve = kTrap ? (a.round == 2 ? (uint32_t)kDeferred : (4u | ((uint32_t)kDeferred << 4)))
                                  : a.round == 2 ? (uint32_t)kReturned : serve_hot ? hot_lists : cold_lists;
-    const int      n_serve = kTrap ? (a.round == 2 ? 1 : 2) : a.round == 2 ? 1 : serve_hot ? n_hot : 2;
+    // Overlap mode (trap kernel, one exciton per lane): the lane kernel of this launch runs at the same time and is still
+    // filling the deferred list.  A lane that finds class 4 exhausted claims the next SLOT of that list -- claimed or not,
+    // slots fill in order -- and polls it until the lane kernel publishes an exciton there (hand_over) or has finished
+    // without reaching it.
+    const bool     overlap = kTrap && G == 1 && a.overlap != 0;
+    const int      n_serve = kTrap ? ((a.round == 2 || overlap) ? 1 : 2) : a.round == 2 ? 1 : serve_hot ? n_hot : 2;
+    bool           polling = false;
+    uint32_t       slot = 0, poll_it = 0;
+    auto claim_slot = [&](bool want) {  // call with the whole warp
+      const unsigned m = __ballot_sync(kFullMask, want);
+      if (m) {
+        unsigned long long base = 0;
+        const int          first = __ffs(m) - 1;
+        if (lane == first) base = atomicAdd(a.q.head + kDeferred, (unsigned long long)__popc(m));
+        base = __shfl_sync(kFullMask, base, first);
+        if (want) {
+          const unsigned long long mine = base + (unsigned long long)__popc(m & lt_mask);
+          slot = (uint32_t)mine;
+          polling = mine < (unsigned long long)a.P;  // an exciton is deferred at most once per launch: later slots stay empty
+        }
+      }
+    };
     int64_t        e64 = 0;
     bool           have = take_exciton(a.q, leader, serve, n_serve, lane, lt_mask, e64, from);
+    if (overlap) claim_slot(!have);
     if (G > 1) {
       have = __shfl_sync(kFullMask, have ? 1 : 0, gbase) != 0;
       e64 = __shfl_sync(kFullMask, e64, gbase);
@@ -404,7 +491,28 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
       e = (uint32_t)e64;
       start();
     }
-    while (__any_sync(kFullMask, have)) {
+    while (__any_sync(kFullMask, have || polling)) {
+      if (overlap) {
+        if (polling && (poll_it++ & 3u) == 0u) {
+          const uint32_t* entry = a.q.list[kDeferred] + slot;
+          uint32_t        v = ld_strong(entry);
+          if (v == 0u && ld_acquire(a.sync) >= (uint32_t)a.lane_grid) {  // the lane kernel has finished: the list is final
+            v = ld_strong(entry);
+            if (v == 0u) polling = false;
+          }
+          if (v != 0u) {
+            e = v - 1u;
+            from = kDeferred;
+            polling = false;
+            have = true;
+            start();
+          }
+        }
+        if (!__any_sync(kFullMask, have)) {
+          __nanosleep(400);
+          continue;
+        }
+      }
       bool finished = false, did_event = false, did_step = false;
       if (kInstr) {
         if (have) ++it_busy; else ++it_idle;
@@ -584,11 +692,17 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
       CNTMC_SEG(L, 5);  // step-end path (own, or waiting for the lanes that run it)
       const bool need_e = have && !finished && !walk_finished && !walk_yield && (L.ff <= dt_rem);
       if (need_e) {
-        const double t = L.ff;
-        const Leg    leg = fly(L, a.T, t, false);
-        dt_rem -= t;  // particle.cpp:63
-        const uint32_t room = (kInstr && trace) ? (uint32_t)(a.trace_cap - trace_base) : 0u;
-        after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, room, a.top_entries != 0);
+        // trap-lanes kernel only (option trap_burst): up to `burst` events of the same time step in a row, without a visit to
+        // the warp's step-end path in between.  15 % off the pass over the trapped excitons at 4; on the ordinary lane kernel
+        // the same loop LOSES (2: -3 %, 8: -15 %, profiles/round2_trap_solver.txt), so there it is compiled out.
+        int left = (kTrap && G == 1) ? a.burst : 1;
+        do {
+          const double t = L.ff;
+          const Leg    leg = fly(L, a.T, t, false);
+          dt_rem -= t;  // particle.cpp:63
+          const uint32_t room = (kInstr && trace) ? (uint32_t)(a.trace_cap - trace_base) : 0u;
+          after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, room, a.top_entries != 0);
+        } while (--left > 0 && (L.ff <= dt_rem) && !L.stuck && !(kDefer && L.hop_valid && L.hop.total >= a.deep_rate));
         did_event = true;
       }
       CNTMC_SEG(L, 7);  // waiting for the other lanes of the warp to finish their events
@@ -620,7 +734,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
           if (finished) cls = activity_class(hop_info(L, a.T).total * a.dt, a.deep_thr);
         }
         file_excitons(a.q, finished && leader, cls, e, lane, lt_mask);
-        if (!kTrap && deep_on) hand_over(a.q, 0, defer, e, lane, lt_mask);
+        if (!kTrap && deep_on) hand_over(a.q, 0, defer, e, lane, lt_mask, a.overlap != 0);
         if (kTrap && a.yield_on) hand_over(a.q, 1, yield && leader, e, lane, lt_mask);
         bool got = take_exciton(a.q, release && leader, serve, n_serve, lane, lt_mask, e64, from);
         if (G > 1) {
@@ -635,6 +749,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
             start();
           }
         }
+        if (overlap) claim_slot(release && !got);
         if (kInstr && t_dry == 0 && __any_sync(kFullMask, release && !got)) t_dry = global_ns();
       }
     }
@@ -683,6 +798,13 @@ __global__ void __launch_bounds__(128, kMinBlocks) kubo_kernel(const KuboArgs a)
   // they live in shared memory (one slot per thread) so that the event path does not carry 12 registers of them.
   __shared__ double s_delta[3][128], s_old[3][128];
   hop_loop<Draws, kInstr, 1, kDefer, false>(a, s_delta, s_old);
+  if (kDefer && a.overlap) {  // tell the trap kernel, which runs beside this one, that this block will defer nothing more
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(a.sync, 1u);
+    }
+  }
 }
 // the trap solver: class 4 of the previous launch and the excitons kubo_kernel deferred in this one
 template <bool kInstr>
@@ -693,7 +815,7 @@ __global__ void __launch_bounds__(128, 4) deep_kernel(const KuboArgs a) {
 // the same lists served one exciton per lane by the generic loop: warps that hold trapped excitons only (experiment, option
 // deep_group = 1)
 template <bool kInstr>
-__global__ void __launch_bounds__(128, 5) trap_lanes_kernel(const KuboArgs a) {
+__global__ void __launch_bounds__(128, 4) trap_lanes_kernel(const KuboArgs a) {
   __shared__ double s_delta[3][128], s_old[3][128];
   hop_loop<PhiloxDraws, kInstr, 1, false, true>(a, s_delta, s_old);
 }

@@ -23,6 +23,29 @@ def _fail(L, code=-1):
     raise CntmcError(code, L.cntmc_davoody_last_error().decode())
 
 
+def fp64_peak(device: int = 0) -> float:
+    """Measured FP64 fused multiply-add peak of a device in TFLOP/s: the denominator of the table kernel's roofline."""
+    L = _lib.load()
+    out = np.zeros(1, np.float64)
+    if L.cntmc_fp64_peak(device, _p(out)) != 0:
+        _fail(L)
+    return float(out[0])
+
+
+def hermitian_eig(a: np.ndarray):
+    """(w ascending, V with eigenvectors in its columns) of a complex Hermitian matrix: the solver that stands in for
+    arma::eig_sym (cnt.cpp:950-962) in the tube physics, csrc/herm_eig.h."""
+    L = _lib.load()
+    a = np.ascontiguousarray(a, np.complex128)
+    n = a.shape[0]
+    assert a.shape == (n, n)
+    w = np.zeros(n, np.float64)
+    v = np.zeros((n, n), np.complex128)
+    if L.cntmc_hermitian_eig(n, _p(a.view(np.float64)), _p(w), _p(v.view(np.float64))) != 0:
+        _fail(L)
+    return w, v
+
+
 class Tube:
     def __init__(self, n: int, m: int, length_cells: int):
         self.L = _lib.load()

@@ -179,7 +179,12 @@ int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites);
  * deep_thr     Gamma*dt from which an exciton is handed to the trap solver, a second kernel that walks trapped excitons
  *              from a register-resident window of site records (default 0 = off: bit-identical results, but slower on
  *              every workload measured so far); deep_blocks (blocks per SM of its launch, default 4), deep_rounds
- *              (2: it hands excitons that left their trap back to the lanes once per launch; default 2)
+ *              (2: it hands excitons that left their trap back to the lanes once per launch; default 2); deep_group (8: the
+ *              window walk; 1: the ordinary loop, one exciton per lane, in warps that hold trapped excitons only) with
+ *              trap_burst (deep_group 1: events a lane may run in a row, default 1), deep_overlap (deep_group 1: the trap
+ *              kernel runs beside the lane kernel of the same launch on a stream of its own and takes the deferred excitons
+ *              while they arrive) and overlap_trap_blocks (its blocks per SM, 1..4).  All measured, none a gain:
+ *              profiles/round2_trap_solver.txt
  * csr_warp     1 (default): the table's fill pass runs one warp per row; 0: one thread per row (the cross-check)
  * host_slices  cntmc_kubo_step_host_state steps the uploaded population in this many slices on their own streams so that
  *              the copies of one overlap the kernels of the others (default 4; populations below 65536 per slice: 1)
@@ -245,6 +250,13 @@ int  cntmc_multi_step(cntmc_multi_t* m, double dt, int64_t nsteps, int64_t* pop_
 typedef struct cntmc_tube     cntmc_tube_t;
 typedef struct cntmc_transfer cntmc_transfer_t;
 const char* cntmc_davoody_last_error(void);
+/* arma::eig_sym as cnt.cpp:950-962 uses it (eigenvalues ascending, eigenvectors in the columns of V; the reference's is LAPACK
+ * zheevd behind Armadillo, this is csrc/herm_eig.h, cyclic Jacobi): a is n x n row-major {re, im} pairs, w [n], v like a.  Host
+ * only; exported so that the CPU suite can pin the solver to LAPACK (tests/test_davoody_host.py) */
+int cntmc_hermitian_eig(int n, const double* a_re_im, double* w, double* v_re_im);
+/* measurement aid, no reference counterpart: FP64 fused multiply-add peak of a device in TFLOP/s (a register-only kernel), the
+ * denominator of the table kernel's roofline in tools/davoody_bench.py */
+int cntmc_fp64_peak(int device, double* tflops);
 
 /* cnt::cnt(json, dir) + cnt::calculate_exciton_dispersion  exciton_transfer/cnt.h:159-193, cnt.cpp:1056-1081: chirality
  * (n, m), length in cnt unit cells ("length": [L, "cnt unit cells"]).  Host only; writes no files.  NULL on failure. */

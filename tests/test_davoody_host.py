@@ -43,6 +43,31 @@ def test_tube_against_the_reference_code_live():
             assert (ik0, nkc) == (ik0r, nkcr) and np.array_equal(e, er)
 
 
+def test_eigensolver_against_lapack():
+    """The one piece the davoody oracle shares with the product is the Hermitian eigensolver (the reference calls LAPACK through
+    arma::eig_sym, absent here; the stand-in it is compiled against uses csrc/herm_eig.h too).  Pin it to LAPACK directly:
+    numpy.linalg.eigh is zheevd, the routine behind eig_sym."""
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 8, 21, 40, 64):
+        for kind in range(3):
+            a = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+            a = a + a.conj().T
+            if kind == 1 and n > 2:   # degenerate and clustered spectra, as K_cm = 0 blocks have
+                q, _ = np.linalg.qr(a)
+                d = np.repeat(rng.normal(size=(n + 1) // 2), 2)[:n]
+                a = (q * d) @ q.conj().T
+                a = (a + a.conj().T) / 2
+            if kind == 2:             # the scale of a Bethe-Salpeter kernel in joules
+                a = a * 1.6e-19
+            w, v = dv.hermitian_eig(a)
+            w_ref = np.linalg.eigh(a)[0]
+            scale = np.abs(w_ref).max()
+            assert np.all(np.diff(w) >= 0)
+            assert np.abs(w - w_ref).max() <= 4e-15 * n * scale
+            assert np.abs(a @ v - v * w).max() <= 1e-14 * n * scale          # A V = V diag(w)
+            assert np.abs(v.conj().T @ v - np.eye(n)).max() <= 1e-14 * n     # orthonormal columns
+
+
 def test_lattice_numbers_of_known_tubes():
     t = dv.Tube(4, 2, 10)  # the shipped input.json's tube (SURVEY.md: Nu=28, t=(4,-5), M=6, Q=2, 140 k x 2 mu)
     assert (t.Nu, t.M, t.Q, t.nk, t.sites) == (28, 6, 2, 140, 280)

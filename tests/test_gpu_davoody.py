@@ -89,7 +89,8 @@ def test_input_json_table_full_size():
             diag = np.array([t0[k, p, p + s] for p in range(max(0, -s), min(11, 11 - s))])
             assert np.all(np.abs(diag - diag[0]) <= 1e-9 * diag[0])
     # identical tubes, parallel axes: swapping donor and acceptor mirrors the axis shifts
-    assert np.allclose(t0, np.transpose(t0, (0, 2, 1)), rtol=1e-9, atol=0)
+    # (the reference's own table has this symmetry to 6e-9 only: its rotation uses pi = 3.141592)
+    assert np.allclose(t0, np.transpose(t0, (0, 2, 1)), rtol=1e-7, atol=0)
     # nearest placement transfers fastest, and the rate falls with distance
     assert rates.max() == rates[:, 0].max() and np.all(rates[:, 0].mean(axis=(1, 2)) > rates[:, -1].mean(axis=(1, 2)))
     if f1.available():
@@ -106,17 +107,27 @@ def test_engine_builds_its_davoody_table_at_init(golden_small):
                "axis shift 1 [m]": [-10e-9, 10e-9, 3], "axis shift 2 [m]": [-10e-9, 10e-9, 3]})
     cnts = {"directory": "~/x", "comment": "c", "2": {"chirality": [5, 3], "length": [2, "cnt unit cells"]},
             "1": {"chirality": [4, 2], "length": [6, "cnt unit cells"]}}
+    # short tubes transfer slowly: a first build measures the film's rates, then the velocity is set so that a free flight
+    # (v / Gamma) spans about two sites and the time step so that it holds some twenty events
+    e0 = Engine({"cnts": cnts, "exciton monte carlo": mc})
+    e0.set_mesh(g.pos_nm, g.orient)
+    e0.kubo_init()
+    gamma = e0.sites()["max_rate"]
+    gamma_med = float(np.median(gamma[gamma > 0]))
+    mc["exciton velocity [m/s]"] = 1e-8 * gamma_med
+    dt = 20.0 / gamma_med
     e = Engine({"cnts": cnts, "exciton monte carlo": mc})
     e.set_mesh(g.pos_nm, g.orient)
     e.kubo_init()
-    theta, z, a1, a2, rates = e.rate_table()
+    tab = e.rate_table()
+    theta, z, a1, a2, rates = (tab[k] for k in ("theta", "z", "a1", "a2", "rates"))
     x = dv.Transfer(tube((4, 2, 6)), tube((4, 2, 6)))      # the first tube in key order, to itself
     axes = dv.table_axes(mc)
     for got, want in zip((theta, z, a1, a2), axes):
         assert np.array_equal(got, want)
     assert np.array_equal(rates, x.table(*axes))
     e.kubo_create_particles(g.P, seed=g.seed)
-    msd = e.kubo_step(g.dt, 50)
+    msd = e.kubo_step(dt, 50)
     assert e.hops() > 0 and np.all(np.isfinite(msd))
     # the same table installed by hand gives the same run
     e2 = Engine(mc)
@@ -124,7 +135,7 @@ def test_engine_builds_its_davoody_table_at_init(golden_small):
     x.install(e2, *axes)
     e2.kubo_init()
     e2.kubo_create_particles(g.P, seed=g.seed)
-    assert np.array_equal(msd, e2.kubo_step(g.dt, 50)) and e2.hops() == e.hops()
+    assert np.array_equal(msd, e2.kubo_step(dt, 50)) and e2.hops() == e.hops()
 
 
 def test_driver_runs_a_davoody_input(tmp_path, golden_small):
@@ -144,9 +155,10 @@ def test_driver_runs_a_davoody_input(tmp_path, golden_small):
     r = subprocess.run([B.DRIVER, path], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     out = str(tmp_path / "out")
-    rates = open(os.path.join(out, "scat_table.rates.dat")).read().split()
-    assert rates[0] == "sizes:" and [int(v) for v in rates[1:5]] == [3, 3, 3, 3]
+    lines = open(os.path.join(out, "scat_table.rates.dat")).read().split("\n")
+    assert lines[0] == "sizes:" and lines[2] == "3,3,3,3"   # scattering_struct.h:56-94
+    rates = lines[:4] + [v for v in lines[4:] if v.strip()]
     x = dv.Transfer(tube((4, 2, 4)), tube((4, 2, 4)))
     want = x.table(*dv.table_axes(mc))
-    got = np.array([float(v) for v in rates[5:]]).reshape(3, 3, 3, 3)
+    got = np.array([float(v) for v in rates[4:]]).reshape(3, 3, 3, 3)
     assert np.array_equal(got, want)

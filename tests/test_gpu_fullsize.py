@@ -51,6 +51,10 @@ def test_full_size_properties(c2):
     e2, _, q1, msd2 = run(c2, dict(chunk_steps=16, hot_pct=0, occupancy=6, deep_thr=0), steps=(5, STEPS - 5))
     assert all(np.array_equal(p1[k], q1[k]) for k in p1)
     assert np.array_equal(msd, msd2) and e2.hops() == e.hops()
+    # so does running the trap kernel beside the lane kernel, with excitons handed over while both run
+    e3, _, r1, msd3 = run(c2, dict(chunk_steps=64, deep_thr=8, deep_group=1, deep_overlap=1, trap_burst=4))
+    assert all(np.array_equal(p1[k], r1[k]) for k in p1)
+    assert np.array_equal(msd, msd3) and e3.hops() == e.hops()
     # a shard of the population run alone follows the same trajectories (what multi-GPU sharding relies on)
     first, count = 700_000, 4096
     _, _, s1, _ = run(c2, dict(chunk_steps=7), first=first, count=count)

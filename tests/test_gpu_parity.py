@@ -112,7 +112,11 @@ def test_chunking_scheduling_and_occupancy_do_not_change_results():
                  dict(chunk_steps=8, hot_pct=30, occupancy=6, deep_thr=1, deep_blocks=2),
                  dict(top_entries=0), dict(top_entries=1, chunk_steps=16, deep_thr=0), dict(top_entries=0, runs=0, hot_pct=50),
                  dict(dirs=0, chunk_steps=9, deep_thr=30), dict(chunk_steps=40, deep_thr=2, deep_rounds=2), dict(chunk_steps=64, deep_thr=9, deep_rounds=1),
-                 dict(chunk_steps=64, deep_thr=8, deep_group=1), dict(chunk_steps=11, deep_thr=16, deep_group=1, deep_rounds=1), dict(runs=0, hot_pct=5, chunk_steps=33, deep_thr=16)):
+                 dict(chunk_steps=64, deep_thr=8, deep_group=1), dict(chunk_steps=11, deep_thr=16, deep_group=1, deep_rounds=1), dict(runs=0, hot_pct=5, chunk_steps=33, deep_thr=16),
+                 # event bursts; the trap kernel beside the lane kernel of the same launch (in-launch hand-over)
+                 dict(chunk_steps=64, deep_thr=8, deep_group=1, trap_burst=4), dict(chunk_steps=64, deep_thr=8, deep_group=1, trap_burst=4, deep_overlap=1),
+                 dict(chunk_steps=9, deep_thr=16, deep_group=1, deep_overlap=1, overlap_trap_blocks=2, trap_burst=3),
+                 dict(chunk_steps=64, deep_thr=1, deep_group=1, deep_overlap=1, trap_burst=64, hot_pct=50)):
         e = Engine(mc)
         e.set_mesh(pos, ori)
         for k, v in opts.items():

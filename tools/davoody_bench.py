@@ -16,6 +16,8 @@ with_ref = "--ref" in sys.argv
 mc = {"zshift [m]": [1.5e-9, 10e-9, 11], "axis shift 1 [m]": [-10e-9, 10e-9, 11], "axis shift 2 [m]": [-10e-9, 10e-9, 11],
       "theta [degrees]": [0, 180, 21]}
 axes = dv.table_axes(mc)
+peak = dv.fp64_peak(0)
+print(json.dumps({"fp64_fma_peak_tflops_measured": peak}), flush=True)
 for spec in [(4, 2, 10), (4, 2, 20), (4, 2, 40), (6, 5, 10), (4, 2, 80)]:
     t = dv.Tube(*spec)
     t0 = time.time()
@@ -35,6 +37,8 @@ for spec in [(4, 2, 10), (4, 2, 20), (4, 2, 40), (6, 5, 10), (4, 2, 80)]:
     line = {"tube": spec, "sites": t.sites, "tube_build_s": t.build_seconds, "transfer_setup_s": t_x, "pairs": info["pairs"],
             "donor_kcm": info["donor_kcm"], "kcm_per_pass": info["kcm_per_pass"], "threads": info["threads"], "table_kernel_ms": min(ms),
             "site_pairs_per_s": n_place * site_pairs * passes / (min(ms) * 1e-3), "fp64_tflops_counted": flop / (min(ms) * 1e-3) / 1e12}
+    line["roofline"] = {"bound": "fp64", "achieved": line["fp64_tflops_counted"], "peak": peak, "unit": "TFLOP/s",
+                        "frac": line["fp64_tflops_counted"] / peak}
     if with_ref and t.sites <= 1200:
         from oracle import f1
         r = f1.RefTube(*spec)
