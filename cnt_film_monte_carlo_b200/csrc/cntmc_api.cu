@@ -714,9 +714,20 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   h->d_hand_list[1].alloc((size_t)h->P);
   h->d_hand_count.alloc(2);
   if (deep) {
+    const bool fresh = h->d_cur_step.n < (size_t)h->P || !h->d_cur_step.p;
     h->d_cur_dt.alloc((size_t)h->P); h->d_cur_ox.alloc((size_t)h->P); h->d_cur_oy.alloc((size_t)h->P); h->d_cur_oz.alloc((size_t)h->P);
     h->d_cur_step.alloc((size_t)h->P);
     h->d_cur_nevent.alloc((size_t)h->P);
+    if (fresh) {
+      // Every cursor is written by the lane that defers its exciton before anybody reads it.  The arrays are zeroed once all the
+      // same: in overlap mode the reader is another kernel running at the same time, ordered by release / acquire on the list
+      // entry, and compute-sanitizer's initcheck (whose shadow memory is not part of that ordering) otherwise reports a handful
+      // of first-ever cursor reads per run, a different handful every time, with bit-identical results.
+      CUDA_CHECK(cudaMemsetAsync(h->d_cur_step.p, 0, (size_t)h->P * sizeof(int32_t), st));
+      CUDA_CHECK(cudaMemsetAsync(h->d_cur_nevent.p, 0, (size_t)h->P * sizeof(uint32_t), st));
+      for (DevBuf<double>* b : {&h->d_cur_dt, &h->d_cur_ox, &h->d_cur_oy, &h->d_cur_oz})
+        CUDA_CHECK(cudaMemsetAsync(b->p, 0, (size_t)h->P * sizeof(double), st));
+    }
   }
   auto lists = [&](int read_buf) {
     ClassLists q{};
