@@ -49,6 +49,12 @@ WORKLOADS = {
                text="C4: dense film, 20 000 tubes x 250 sites (5e6 sites, ~1.4e9 table entries), HBM-resident rate table"),
     "C5": dict(film="C2", mode="contacts", dt=DT, trim=TRIM_WIDE, excitons=None, intervals=25, chunk=64, steps=5, scaling="weak",
                text="C5: contact-driven transport on the C2 film, contact population scaled to ~1.25e8 excitons alive per GPU"),
+    # not a BASELINE config: the step before the hot path, measured to the same contract
+    "F1": dict(film=None, mode="davoody", dt=DT, tube=(4, 2, 10), steps=20, scaling="weak",
+               grids={"theta [degrees]": [0, 180, 21], "zshift [m]": [1.5e-9, 10e-9, 11], "axis shift 1 [m]": [-10e-9, 10e-9, 11],
+                      "axis shift 2 [m]": [-10e-9, 10e-9, 11]},
+               text="F1: the davoody rate table of the reference's input.json -- (4,2) tube x 10 unit cells to itself, 21 x 11 x 11 x 11 "
+                    "placements, exciton_transfer::first_order per entry"),
 }
 WORKLOAD = WORKLOADS["C2"]["text"]
 
@@ -600,6 +606,117 @@ def run_contacts(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ---- F1: the davoody rate table -------------------------------------------------------------------------------------------
+def davoody_reference_sample(wl, n_theta):
+    """The reference's own first_order (oracle/_ref/libf1.so, its loop nest over theta under OpenMP like monte_carlo.cpp:107-137) on
+    the first n_theta angles x 1 z shift x 2 x 2 axis shifts of the workload's table.  Returns (entries, seconds, threads)."""
+    from cnt_film_monte_carlo_b200 import davoody as dv
+    from oracle import f1
+    if not f1.available():
+        return None
+    theta, z, a1, a2 = dv.table_axes(wl["grids"])
+    r = f1.RefTube(*wl["tube"])
+    f1.table(r, r, theta[:1], z[:1], a1[:1], a2[:1])  # first call builds the matched state pairs
+    t0 = time.perf_counter()
+    out = f1.table(r, r, theta[:n_theta], z[:1], a1[4:6], a2[4:6])
+    return out.size, time.perf_counter() - t0, min(n_theta, os.cpu_count() or 1)
+
+
+def run_davoody(args, rank, world, local_rank):
+    """One step = the whole table of the workload through the C ABI (cntmc_transfer_table: host axes in, host rates out).  `value`
+    counts the placement kernel alone (CUDA events around it on its stream: the placements are in device memory by then), `e2e`
+    the whole call.  Ranks build replicas (the entries are independent; nothing to exchange)."""
+    wl = WORKLOADS["F1"]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_theta = min(21, max(2, os.cpu_count() or 1))
+        got = davoody_reference_sample(wl, n_theta)
+        if got is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libf1.so is not built on this box"}))
+            return
+        vals = [davoody_reference_sample(wl, n_theta) for _ in range(max(1, min(args.steps, 5)))]
+        n, sec = sum(v[0] for v in vals), sum(v[1] for v in vals)
+        sample = "%d table entries per step (%d angles x 1 x 2 x 2), reference first_order under OpenMP over theta" % (vals[0][0], n_theta)
+        print(json.dumps({
+            "impl": "reference", "metric": "davoody table entries/sec", "value": n / sec, "unit": "entries/s", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": 1, "ms_per_step": 1e3 * sec / len(vals), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": wl["text"], "sample": sample},
+            "cpu_baseline": {"value": n / sec, "unit": "entries/s", "cores": vals[0][2], "kind": "reference", "sample": sample},
+            "e2e": {"value": n / sec, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    torch, dist, dev = dist_setup(local_rank, world)
+    from cnt_film_monte_carlo_b200 import davoody as dv
+
+    t0 = time.perf_counter()
+    tube = dv.Tube(*wl["tube"])
+    x = dv.Transfer(tube, tube, device=local_rank)
+    t_setup = time.perf_counter() - t0
+    axes = dv.table_axes(wl["grids"])
+    n_entries = int(np.prod([len(a) for a in axes]))
+    info = x.info()
+    passes = -(-info["donor_kcm"] // info["kcm_per_pass"])
+    # FP64 operations the formula needs per site pair and pass: 3 sub, 3 mul, 2 add, sqrt, div + 2 fused multiply-adds per K_cm
+    flop_per_step = float(n_entries) * tube.sites * tube.sites * passes * (10 + 4 * info["kcm_per_pass"])
+    for _ in range(max(3, args.warmup)):
+        x.table(*axes)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    kernel_ms, wall = 0.0, 0.0
+    for _ in range(args.steps):
+        flush.fill_(0)
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        rates = x.table(*axes)       # synchronous: returns after the D2H of the rates
+        wall += time.perf_counter() - w0
+        kernel_ms += x.info()["last_kernel_ms"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([kernel_ms, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms, wall = float(t[0].item()), float(t[1].item())
+    value = world * n_entries * args.steps / (kernel_ms * 1e-3)
+    achieved = flop_per_step * args.steps / (kernel_ms * 1e-3) / 1e12
+    peak = dv.fp64_peak(local_rank)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        got = davoody_reference_sample(wl, min(21, max(2, os.cpu_count() or 1)))
+        if got is not None:
+            cpu = {"value": got[0] / got[1], "unit": "entries/s", "cores": got[2], "kind": "reference",
+                   "sample": "%d table entries (%d angles x 1 x 2 x 2) in %.1f s" % (got[0], got[2], got[1])}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "davoody table entries/sec", "value": value, "unit": "entries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["text"], "entries_per_step": n_entries, "sites_per_tube": tube.sites, "state_pairs": info["pairs"],
+                       "donor_kcm": info["donor_kcm"], "kcm_per_pass": info["kcm_per_pass"], "threads_per_block": info["threads"],
+                       "tube_and_transfer_setup_s": round(t_setup, 3), "rate_min_max": [float(rates.min()), float(rates.max())],
+                       "l2": "flushed between timed steps (256 MiB fill, outside the timed calls)",
+                       "parallelism": "replicas x%d (independent table entries, no exchange)" % world},
+            "clocks": clocks,
+            "e2e": {"value": world * n_entries * args.steps / wall, "unit": "entries/s", "h2d_bytes_per_step": 5 * 8 * n_entries,
+                    "d2h_bytes_per_step": 8 * n_entries, "steps": args.steps},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "measured on this GPU (cntmc_fp64_peak: register-only fused multiply-add kernel)",
+                         "kernel": "placement_rate_kernel<%d>" % info["kcm_per_pass"], "kernel_ms_per_launch": kernel_ms / args.steps,
+                         "note": "counted: 10 + 4 K FP64 operations per site pair; a correctly rounded 1/sqrt is ~24 of the ~40 FP64 "
+                                 "instructions per pair and counts as 2 (ncu: FP64 pipe 66 % busy, profiles/round2_davoody_*)"},
+            "cpu_baseline": cpu}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -628,7 +745,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if WORKLOADS[args.workload]["mode"] == "davoody":
+        run_davoody(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank)
     else:
         run_ours(args, rank, world, local_rank)

@@ -120,6 +120,8 @@ int f1_table(int donor, int acceptor, int nth, const double* theta, int nz, cons
              const double* a2, double* rate) {
   try {
     exciton_transfer ex_transfer(*g_cnts[donor], *g_cnts[acceptor]);
+    // the reference's own team: "#pragma omp parallel" + "#pragma omp for" over theta (monte_carlo.cpp:107-112)
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < nth; ++i)
       for (int k = 0; k < nz; ++k)
         for (int p = 0; p < n1; ++p)
