@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <atomic>
 #include <complex>
 #include <cstdint>
 #include <numeric>
@@ -47,8 +48,8 @@ struct Consts {
 
 // independent iterations over host threads (each iteration owns its outputs, so the result does not depend on the split)
 template <typename F>
-inline void parallel_for(int n, F&& body) {
-  const int workers = std::max(1, std::min<int>(n / 16, (int)std::thread::hardware_concurrency()));
+inline void parallel_for(int n, int grain, F&& body) {
+  const int workers = std::max(1, std::min<int>(n / std::max(1, grain), (int)std::thread::hardware_concurrency()));
   if (workers <= 1) {
     for (int i = 0; i < n; i++) body(i);
     return;
@@ -294,7 +295,7 @@ class Tube {
     const double coeff = std::pow(4. * Consts::pi * Consts::eps0() * Upp / Consts::q0() / Consts::q0(), 2);
     const double count = double(2 * Nu * span);
     vq.assign((size_t)nq * n_muq * 4, cplx(0, 0));
-    parallel_for(nq, [&](int iq_idx) {
+    parallel_for(nq, 16, [&](int iq_idx) {
       const int iq = iq_begin + iq_idx;
       for (int mu_idx = 0; mu_idx < n_muq; mu_idx++) {
         const int  mu = mu_begin + mu_idx;
@@ -335,7 +336,7 @@ class Tube {
       const cplx s = std::conj(w(ik, mu, band, 0)) * w(ik2, mu2, band2, 0) + std::conj(w(ik, mu, band, 1)) * w(ik2, mu2, band2, 1);
       return std::pow(std::abs(s), 2);
     };
-    parallel_for(nq, [&](int iq_idx) {
+    parallel_for(nq, 16, [&](int iq_idx) {
       const int iq = iq_begin + iq_idx;
       for (int mu_idx = 0; mu_idx < n_muq; mu_idx++) {
         const int mu_q = mu_begin + mu_idx;
@@ -404,15 +405,16 @@ class Tube {
       return acc;
     };
 
-    std::vector<cplx>   k11((size_t)nr * nr), k12((size_t)nr * nr), kx((size_t)nr * nr), H((size_t)nr * nr), V((size_t)nr * nr);
-    std::vector<double> E(nr);
-    const double        inv_sqrt2 = 1 / std::sqrt(2.);
+    const double inv_sqrt2 = 1 / std::sqrt(2.);
+    std::atomic<bool> failed(false);
 
-    for (int ik_cm = -nr; ik_cm < nr; ik_cm++) {
-      const int idx = ik_cm + nr;
-      std::fill(k11.begin(), k11.end(), cplx(0, 0));
-      std::fill(k12.begin(), k12.end(), cplx(0, 0));
-      std::fill(kx.begin(), kx.end(), cplx(0, 0));
+    // the 2 nr centre-of-mass momenta are independent problems (three eigen-decompositions each): one host thread each, every
+    // iteration writes its own slices of the outputs, so the bits do not depend on how the iterations are split
+    parallel_for(nk_cm, 1, [&](int idx) {
+      const int ik_cm = idx - nr;
+      std::vector<cplx>   k11((size_t)nr * nr, cplx(0, 0)), k12((size_t)nr * nr, cplx(0, 0)), kx((size_t)nr * nr, cplx(0, 0)), H((size_t)nr * nr),
+          V((size_t)nr * nr);
+      std::vector<double> E(nr);
       // valley 1 carries the electron index, valley 2 the hole index (its electron follows from K_cm)
       auto pair_v1 = [&](int i) {
         const int ik_c = relev[0][i][0], mu = relev[0][i][1];
@@ -448,7 +450,7 @@ class Tube {
       symmetrise(kx);
 
       auto solve = [&](ExcitonKind kind, double sign_tail) {
-        if (hermitian_eig(nr, H.data(), E.data(), V.data()) < 0) throw std::runtime_error("exciton eigenproblem did not converge");
+        if (hermitian_eig(nr, H.data(), E.data(), V.data()) < 0) failed = true;
         Exciton& ex = excitons[kind];
         for (int s = 0; s < nr; s++) {
           ex.energy[(size_t)idx * nr + s] = E[s];
@@ -477,7 +479,8 @@ class Tube {
           pi[(size_t)(nk_c - 1 - a) * 4 + c] = second[c];
         }
       }
-    }
+    });
+    if (failed) throw std::runtime_error("exciton eigenproblem did not converge");
   }
 
   // k_c - k_c' folded into [0, nk): the direct term looks v(q) up at that index (the band range starts at 0)
