@@ -117,6 +117,8 @@ class monte_carlo:
         self._say("exciton velocity [m/s]: %g" % float(self._json_prop["exciton velocity [m/s]"]))
         self._engine.load_mesh(self._input_directory)
         self._engine.kubo_init()
+        if self._json_prop.get("rate type") == "davoody":
+            self.save_scat_table()  # create_davoody_scatt_table leaves its table in the output directory (monte_carlo.cpp:150)
         d = self._engine.domain() * 1e9
         self._say("\nsimulation domain AFTER trimming:\n    x (%+f , %+f) [nm]\n    y (%+f , %+f) [nm]\n    z (%+f , %+f) [nm]\n"
                   % (d[0], d[3], d[1], d[4], d[2], d[5]))
@@ -174,6 +176,8 @@ class monte_carlo:
         """monte_carlo.h:157-195 (the reference hard-codes the contact populations 1100 and 0, :191-192)."""
         self._engine.load_mesh(self._input_directory)
         self._engine.init(c1_pop, c2_pop, seed=self._seed)
+        if self._json_prop.get("rate type") == "davoody":
+            self.save_scat_table()  # monte_carlo.cpp:150
         self._n_seg = self._engine.number_of_segments()
         self._area = self._engine.area()
         self._domain = self._engine.domain()
