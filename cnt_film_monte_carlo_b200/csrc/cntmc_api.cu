@@ -569,7 +569,7 @@ void common_init(cntmc_t* h) {
       rec.inv_total = row.empty() ? 0.0 : 1. / acc;
       struct CumView {
         const RowEntry* r;
-        double          operator[](uint32_t k) const { return r[k].cum; }
+        __host__ __device__ double operator[](uint32_t k) const { return r[k].cum; }  // build_guide is a host-device template
       };
       build_guide(CumView{row.data()}, (uint32_t)row.size(), acc, rec.guide);
       top.store(rec.top);

@@ -218,18 +218,16 @@ cntmc_transfer_t* cntmc_transfer_create(const cntmc_tube_t* donor, const cntmc_t
     h->Kd_pad = (Kd + h->chunk - 1) / h->chunk * h->chunk;
     // threads = acceptor sites per pass: the number of passes (of at most 320 threads) that leaves the fewest idle threads
     // (280 sites: one pass of 288, not 256 + 24 and not 2 x 160; every pass re-stages the donor tiles)
-    int best_passes = 1, best_threads = 0;
+    int  best_threads = 0;
     long best_slots = -1;
     for (int passes = (Na + 319) / 320; passes <= (Na + 319) / 320 + 3; passes++) {
       const int  t = std::max(32, ((Na + passes - 1) / passes + 31) / 32 * 32);
       const long slots = (long)t * passes;
       if (t <= 320 && (best_slots < 0 || slots < best_slots)) {
         best_slots = slots;
-        best_passes = passes;
         best_threads = t;
       }
     }
-    (void)best_passes;
     h->threads = best_threads;
     h->smem = placement_smem_bytes(h->chunk, h->threads, h->Kd_pad, Ka);
     require(h->smem <= 200 * 1024, "too many distinct K_cm among the matched states for one thread block's shared memory");
