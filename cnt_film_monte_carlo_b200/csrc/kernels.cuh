@@ -496,7 +496,9 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
         if (polling && (poll_it++ & 3u) == 0u) {
           const uint32_t* entry = a.q.list[kDeferred] + slot;
           uint32_t        v = ld_strong(entry);
-          if (v == 0u && ld_acquire(a.sync) >= (uint32_t)a.lane_grid) {  // the lane kernel has finished: the list is final
+          // the lane kernel has finished: the list is final.  (The relaxed read comes first: an acquire load is followed by an
+          // invalidation of the SM's whole L1, CCTL.IVALL, which the busy lanes of this SM would pay for at every empty poll.)
+          if (v == 0u && ld_strong(a.sync) >= (uint32_t)a.lane_grid && ld_acquire(a.sync) >= (uint32_t)a.lane_grid) {
             v = ld_strong(entry);
             if (v == 0u) polling = false;
           }
