@@ -33,6 +33,8 @@ CASES = [  # donor, acceptor, temperature, broadening meV, number of random plac
     ((4, 2, 10), (4, 2, 14), 300.0, 4.0, 4, []),            # tubes of different length
     ((5, 3, 4), (5, 3, 4), 300.0, 6.5, 4, []),              # another chirality, another broadening
     ((4, 2, 6), (5, 3, 4), 300.0, 4.0, 2, []),              # no energy-matched states: all rates are zero
+    ((4, 2, 10), (5, 3, 4), 300.0, 4.0, 4, []),             # two different chiralities, downhill: rates of 1e10 /s
+    ((4, 2, 10), (6, 5, 3), 300.0, 4.0, 3, []),             # far apart in energy: only the Lorentzian's tail is left (1e-19 /s)
 ]
 
 
