@@ -73,6 +73,7 @@ SIGNATURES = {
     "cntmc_sync": (C.c_int, [V]),
     "cntmc_last_kernel_ms": (D, [V]),
     "cntmc_last_kernel_launches": (I64, [V]),
+    "cntmc_dbg_walk_arith": (C.c_int, [C.c_int, I64, C.c_uint64, V]),
     "cntmc_multi_create": (C.c_int, [CP, C.c_int, V, C.POINTER(V)]),
     "cntmc_multi_destroy": (None, [V]),
     "cntmc_multi_last_error": (CP, [V]),

@@ -631,6 +631,80 @@ void create_common(cntmc_t* h, int64_t P) {
 
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 
+// ---- self-test of the call-free square root and divisions of the chain walk (hop_core.h sqrt_walk / div3_walk) --------------
+// counts[0]: square roots that differ from sqrt(), [1]: quotients that differ from '/', [2]: in-range operands flagged,
+// [3]: out-of-range operands NOT flagged.  Operands: full-range mantissas, exponents over the accepted range, with the
+// numerators of a quotient at most the divisor in magnitude (components of a vector over its norm) or exactly zero.
+__device__ __forceinline__ uint64_t mix64(uint64_t& s) {
+  uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double make_double(uint64_t mant, int exp2, bool neg) {  // (1 + mant / 2^52) * 2^exp2
+  return __longlong_as_double((long long)(((uint64_t)neg << 63) | ((uint64_t)(exp2 + 1023) << 52) | (mant & 0xfffffffffffffull)));
+}
+__global__ void __launch_bounds__(256) walk_arith_kernel(int64_t per_thread, uint64_t seed, unsigned long long* counts) {
+  uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x + 1));
+  unsigned long long bad_sqrt = 0, bad_div = 0, false_flag = 0, missed = 0;
+  for (int64_t it = 0; it < per_thread; ++it) {
+    const uint64_t a = mix64(s), b = mix64(s), c = mix64(s), d = mix64(s), e = mix64(s);
+    // square root: the sum of squares of a separation, any exponent of the accepted range; every 16th a perfect square
+    double x = make_double(a, (int)(b % 799u) - 399, false);
+    if ((b >> 40 & 15u) == 0u) {
+      const double r = make_double(a & 0xffffffc000000ull, ((int)(b % 799u) - 399) / 2, false);  // 26 significant bits: r * r is exact
+      x = r * r;
+    }
+    bool flag = false;
+    const double got = sqrt_walk(x, flag), want = sqrt(x);
+    bad_sqrt += __double_as_longlong(got) != __double_as_longlong(want);
+    false_flag += flag;
+    // divisions: a vector over its norm
+    const int    ed = (int)(c % 711u) - 320;  // the smallest numerator below is 72 binades under the divisor
+    const double den = make_double(c >> 10, ed, false);
+    double       w[3];
+    const uint64_t m[3] = {d, e, a ^ (c << 7)};
+    for (int k = 0; k < 3; ++k) {
+      const int down = (int)((m[k] >> 54) % 9u);           // 0..8: how far below the divisor, in steps of 8 binades
+      w[k] = make_double(m[k], ed - 1 - 8 * down - (int)(m[k] >> 60 & 7u), (m[k] >> 53 & 1u) != 0);
+      if ((m[k] >> 48 & 31u) == 0u) w[k] = (m[k] >> 53 & 1u) ? -0.0 : 0.0;
+      if ((m[k] >> 48 & 31u) == 1u) w[k] = (m[k] >> 53 & 1u) ? -den : den;
+    }
+    double ux, uy, uz;
+    flag = false;
+    div3_walk_dev(w[0], w[1], w[2], den, ux, uy, uz, flag);
+    bad_div += __double_as_longlong(ux) != __double_as_longlong(w[0] / den);
+    bad_div += __double_as_longlong(uy) != __double_as_longlong(w[1] / den);
+    bad_div += __double_as_longlong(uz) != __double_as_longlong(w[2] / den);
+    false_flag += flag;
+    // outside the accepted range: must be flagged
+    if ((it & 255) == 0) {
+      const int    out = (a & 1u) ? 402 + (int)(b % 600u) : -401 - (int)(b % 600u);
+      const double xo = make_double(a, out, false);
+      flag = false;
+      (void)sqrt_walk(xo, flag);
+      missed += !flag;
+      flag = false;
+      div3_walk_dev(w[0], w[1], w[2], xo, ux, uy, uz, flag);
+      missed += !flag;
+      flag = false;
+      div3_walk_dev(w[0], make_double(d, -401 - (int)(b % 600u), false), w[2], den, ux, uy, uz, flag);
+      missed += !flag;
+    }
+  }
+  bad_sqrt = __reduce_add_sync(kFullMask, (unsigned)bad_sqrt);
+  bad_div = __reduce_add_sync(kFullMask, (unsigned)bad_div);
+  false_flag = __reduce_add_sync(kFullMask, (unsigned)false_flag);
+  missed = __reduce_add_sync(kFullMask, (unsigned)missed);
+  if ((threadIdx.x & 31) == 0) {
+    if (bad_sqrt) atomicAdd(counts + 0, bad_sqrt);
+    if (bad_div) atomicAdd(counts + 1, bad_div);
+    if (false_flag) atomicAdd(counts + 2, false_flag);
+    if (missed) atomicAdd(counts + 3, missed);
+  }
+}
+
+
 template <typename Draws, bool kInstr>
 void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st, bool defer) {
   if constexpr (std::is_same<Draws, PhiloxDraws>::value) {
@@ -642,6 +716,7 @@ void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st
   switch (h->opt_occupancy) {
     case 4: kubo_kernel<Draws, 4, kInstr, false><<<grid, 128, 0, st>>>(a); break;
     case 6: kubo_kernel<Draws, 6, kInstr, false><<<grid, 128, 0, st>>>(a); break;
+    case 7: kubo_kernel<Draws, 7, kInstr, false><<<grid, 128, 0, st>>>(a); break;
     default: kubo_kernel<Draws, 5, kInstr, false><<<grid, 128, 0, st>>>(a); break;
   }
 }
@@ -697,7 +772,9 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   // persistent grid: as many 128-thread blocks as the SMs hold at the compiled occupancy, never more than needed
   const int64_t  want = (h->P + 127) / 128;
   // (a slice of a host-resident population takes its share of the block slots: the slices' launches run side by side)
-  const unsigned grid = (unsigned)std::min<int64_t>(want, std::max<int64_t>(1, (int64_t)h->sm_count * h->opt_occupancy / h->grid_share));
+  const char*    dbg_bps = getenv("CNTMC_DBG_BLOCKS_PER_SM");  // experiment: fewer resident blocks than the kernel was compiled for
+  const int64_t  bps = dbg_bps ? atoll(dbg_bps) : h->opt_occupancy;
+  const unsigned grid = (unsigned)std::min<int64_t>(want, std::max<int64_t>(1, (int64_t)h->sm_count * bps / h->grid_share));
   h->last_chunk = chunk;
   h->d_stage.alloc((size_t)chunk * (size_t)h->P);
   h->d_partial.alloc((size_t)chunk * kStageSplits * 4);
@@ -1425,6 +1502,7 @@ static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned 
       switch (h->opt_occupancy) {
         case 4: contact_kernel<PhiloxDraws, 4><<<grid, 128, smem, st>>>(a); break;
         case 6: contact_kernel<PhiloxDraws, 6><<<grid, 128, smem, st>>>(a); break;
+        case 7: contact_kernel<PhiloxDraws, 7><<<grid, 128, smem, st>>>(a); break;
         default: contact_kernel<PhiloxDraws, 5><<<grid, 128, smem, st>>>(a); break;
       }
     }
@@ -1782,7 +1860,7 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
       require(value >= 0 && value <= 100, "hot_pct must be in [0, 100]");
       h->opt_hot_pct = value;
     } else if (k == "occupancy") {
-      require(value >= 4 && value <= 6, "occupancy must be 4 to 6 blocks per SM");
+      require(value >= 4 && value <= 7, "occupancy must be 4 to 7 blocks per SM");
       h->opt_occupancy = value;
     } else if (k == "dirs") {
       h->opt_dirs = value ? 1 : 0;
@@ -1870,6 +1948,29 @@ int cntmc_sync(cntmc_t* h) {
     h->crossings = (int64_t)ctrs[CTR_CROSS];
     h->probes = (int64_t)ctrs[CTR_PROBE];
   });
+}
+int cntmc_dbg_walk_arith(int device, int64_t n, uint64_t seed, int64_t counts[4]) {
+  try {
+    if (counts == nullptr || n < 0) throw std::invalid_argument("bad argument");
+    CUDA_CHECK(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
+    const int     blocks = 148 * 8, threads = 256;
+    const int64_t per_thread = (n + (int64_t)blocks * threads - 1) / ((int64_t)blocks * threads);
+    walk_arith_kernel<<<blocks, threads>>>(per_thread, seed, d);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    unsigned long long hc[4] = {0, 0, 0, 0};
+    if (err == cudaSuccess) err = cudaMemcpy(hc, d, sizeof hc, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (err != cudaSuccess) throw std::runtime_error(cudaGetErrorString(err));
+    for (int k = 0; k < 4; ++k) counts[k] = (int64_t)hc[k];
+    return CNTMC_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return CNTMC_ERR_CUDA;
+  }
 }
 double  cntmc_last_kernel_ms(const cntmc_t* h) { return h->kernel_ms; }
 int64_t cntmc_last_kernel_launches(const cntmc_t* h) { return h->kernel_launches; }

@@ -660,7 +660,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
             if (!at) {
               L.px = px; L.py = py; L.pz = pz;
             }
-            L.hop_valid = false;
+            L.total_valid = false;
           }
         }
       }
@@ -704,16 +704,16 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
           dt_rem -= t;  // particle.cpp:63
           const uint32_t room = (kInstr && trace) ? (uint32_t)(a.trace_cap - trace_base) : 0u;
           after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, room, a.top_entries != 0);
-        } while (--left > 0 && (L.ff <= dt_rem) && !L.stuck && !(kDefer && L.hop_valid && L.hop.total >= a.deep_rate));
+        } while (--left > 0 && (L.ff <= dt_rem) && !L.stuck && !(kDefer && L.total_valid && L.total >= a.deep_rate));
         did_event = true;
       }
       CNTMC_SEG(L, 7);  // waiting for the other lanes of the warp to finish their events
       // trap solver: an exciton that ended a time step on a site that is no trap goes back to the lanes
       bool yield = walk_yield;
-      if (kTrap && a.yield_on && did_step && !did_event && !finished && !L.stuck && !(hop_info(L, a.T).total >= a.deep_rate)) yield = true;
+      if (kTrap && a.yield_on && did_step && !did_event && !finished && !L.stuck && !(site_total(L, a.T) >= a.deep_rate)) yield = true;
       finished = have && (finished || walk_finished || L.stuck);
       // lanes: landed in a deep trap, the trap solver takes over
-      const bool defer = !kTrap && deep_on && did_event && !finished && L.hop_valid && L.hop.total >= a.deep_rate;
+      const bool defer = !kTrap && deep_on && did_event && !finished && L.total_valid && L.total >= a.deep_rate;
       const bool release = finished || defer || yield;
       if (__any_sync(kFullMask, release)) {
         int cls = 0;
@@ -733,7 +733,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
             if (L.stuck) atomicOr(a.flags + FLAG_STUCK, 1);
             if (D.exhausted()) atomicOr(a.flags + FLAG_REPLAY, 1);
           }
-          if (finished) cls = activity_class(hop_info(L, a.T).total * a.dt, a.deep_thr);
+          if (finished) cls = activity_class(site_total(L, a.T) * a.dt, a.deep_thr);
         }
         file_excitons(a.q, finished && leader, cls, e, lane, lt_mask);
         if (!kTrap && deep_on) hand_over(a.q, 0, defer, e, lane, lt_mask, a.overlap != 0);

@@ -205,6 +205,12 @@ int cntmc_sync(cntmc_t* h);
 /* with option "time_kernels" = 1: summed device time and count of the hop-kernel launches of the last step call */
 double  cntmc_last_kernel_ms(const cntmc_t* h);
 int64_t cntmc_last_kernel_launches(const cntmc_t* h);
+/* self-test, no reference counterpart: the hop kernels take particle::fly's |pos - next.pos| (particle.cpp:39) and
+ * normalise(next.pos - pos) (particle.cpp:47) with a square root and a division written out without the compiler's slow-path
+ * calls (csrc/hop_core.h sqrt_walk / div3_walk).  Runs both on about n pseudo-random operands on `device` against the IEEE
+ * operations: counts = {square roots that differ, quotients that differ, in-range operands flagged, out-of-range operands not
+ * flagged}; all four must be zero.  Errors are reported by cntmc_last_error(NULL). */
+int cntmc_dbg_walk_arith(int device, int64_t n, uint64_t seed, int64_t counts[4]);
 
 /* ---- one simulation on several GPUs of one box ---------------------------------------------------------------------------
  * The reference parallelises monte_carlo::kubo_step / step over its particle list with OpenMP (monte_carlo.cpp:320-338,

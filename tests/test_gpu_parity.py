@@ -107,7 +107,7 @@ def test_chunking_scheduling_and_occupancy_do_not_change_results():
     states, msds = [], []
     # the first run is the plain loop (no trap solver); every other scheduling must give the same bits
     for opts in (dict(chunk_steps=64, occupancy=6, deep_thr=0), dict(chunk_steps=7, occupancy=4, deep_thr=16), dict(chunk_steps=1, deep_thr=8, deep_rounds=1),
-                 dict(chunk_steps=200, occupancy=5, deep_thr=0), dict(chunk_steps=64, stage_mb=1, deep_thr=16, deep_blocks=1),
+                 dict(chunk_steps=200, occupancy=5, deep_thr=0), dict(chunk_steps=50, occupancy=7, deep_thr=0), dict(chunk_steps=64, stage_mb=1, deep_thr=16, deep_blocks=1),
                  dict(chunk_steps=8, hot_pct=0, deep_thr=16), dict(chunk_steps=3, hot_pct=100, deep_thr=16, deep_blocks=1),
                  dict(chunk_steps=8, hot_pct=30, occupancy=6, deep_thr=1, deep_blocks=2),
                  dict(top_entries=0), dict(top_entries=1, chunk_steps=16, deep_thr=0), dict(top_entries=0, runs=0, hot_pct=50),
@@ -132,6 +132,18 @@ def test_chunking_scheduling_and_occupancy_do_not_change_results():
     for m in msds[1:]:
         assert np.array_equal(m, msds[0])                          # ensemble sums: fixed-order reduction over exciton index
     assert hops > 5000
+
+
+def test_walk_square_root_and_divisions_are_the_ieee_operations():
+    """The chain walk's call-free square root and divisions (csrc/hop_core.h sqrt_walk / div3_walk) against sqrt() and '/' on the
+    device: 1e9 operand sets over the accepted exponent range (perfect squares, zeros of both signs, |w| = d included) -- no bit
+    differs, nothing in range is flagged, everything outside the range is."""
+    import ctypes
+    from cnt_film_monte_carlo_b200 import _lib
+    counts = (ctypes.c_int64 * 4)()
+    rc = _lib.load().cntmc_dbg_walk_arith(0, 1_000_000_000, 20261018, counts)
+    assert rc == 0, _lib.load().cntmc_last_error(None)
+    assert list(counts) == [0, 0, 0, 0]
 
 
 def test_shortcuts_do_not_change_results_on_a_trimmed_film():
