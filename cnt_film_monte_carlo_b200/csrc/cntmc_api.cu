@@ -210,7 +210,7 @@ struct cntmc_handle {
                                  // the deferred excitons while they arrive (see hop_loop)
   int64_t opt_overlap_trap_blocks = 1;  // blocks per SM of the trap kernel in overlap mode; the lane kernel takes the rest of five
   int64_t opt_deep_rounds = 2;  // 2: the trap solver hands excitons that left their trap back to the lanes once per launch
-  int64_t opt_occupancy = 5;   // resident 128-thread blocks per SM the hop kernel is compiled for (4, 6 or 8)
+  int64_t opt_occupancy = 7;   // resident 128-thread blocks per SM the hop kernel is compiled for (4 to 7; 7 = 72 registers)
   int64_t opt_stage_mb = 0;  // cap on the (step, exciton) staging buffer in MiB; shortens the launches if needed.
                              // 0 = a third of the device memory that is free when the buffer is first sized
   int     sm_count = 0;
@@ -772,7 +772,9 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   // persistent grid: as many 128-thread blocks as the SMs hold at the compiled occupancy, never more than needed
   const int64_t  want = (h->P + 127) / 128;
   // (a slice of a host-resident population takes its share of the block slots: the slices' launches run side by side)
-  const char*    dbg_bps = getenv("CNTMC_DBG_BLOCKS_PER_SM");  // experiment: fewer resident blocks than the kernel was compiled for
+  // (CNTMC_DBG_BLOCKS_PER_SM: fewer resident blocks than the kernel was compiled for -- separates the price of a variant's spills
+  // from the gain of its extra blocks, profiles/round2_trap_solver.txt section 15)
+  const char*    dbg_bps = getenv("CNTMC_DBG_BLOCKS_PER_SM");
   const int64_t  bps = dbg_bps ? atoll(dbg_bps) : h->opt_occupancy;
   const unsigned grid = (unsigned)std::min<int64_t>(want, std::max<int64_t>(1, (int64_t)h->sm_count * bps / h->grid_share));
   h->last_chunk = chunk;
