@@ -301,7 +301,7 @@ void need_rates(const cntmc_t* h) {
   h->max_rate.resize(N);
   h->inv_max_rate.resize(N);
   for (size_t i = 0; i < N; ++i) {
-    h->max_rate[i] = rec[i].total;
+    h->max_rate[i] = rec[i].top.total;
     h->inv_max_rate[i] = rec[i].inv_total;
   }
 }
@@ -565,14 +565,13 @@ void common_init(cntmc_t* h) {
       SiteRec rec;
       CUDA_CHECK(cudaMemcpyAsync(&rec, h->d_site.p + i, sizeof rec, cudaMemcpyDeviceToHost, st));
       CUDA_CHECK(cudaStreamSynchronize(st));
-      rec.total = acc;
       rec.inv_total = row.empty() ? 0.0 : 1. / acc;
       struct CumView {
         const RowEntry* r;
         __host__ __device__ double operator[](uint32_t k) const { return r[k].cum; }  // build_guide is a host-device template
       };
       build_guide(CumView{row.data()}, (uint32_t)row.size(), acc, rec.guide);
-      top.store(rec.top);
+      top.store(rec.top, acc, (uint32_t)row.size());  // with scatterer.h:91 _max_rate
       CUDA_CHECK(cudaMemcpyAsync(h->d_row.p + be[0], row.data(), row.size() * sizeof(RowEntry), cudaMemcpyHostToDevice, st));
       CUDA_CHECK(cudaMemcpyAsync(h->d_site.p + i, &rec, sizeof rec, cudaMemcpyHostToDevice, st));
       CUDA_CHECK(cudaStreamSynchronize(st));
@@ -717,6 +716,7 @@ void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st
     case 4: kubo_kernel<Draws, 4, kInstr, false><<<grid, 128, 0, st>>>(a); break;
     case 6: kubo_kernel<Draws, 6, kInstr, false><<<grid, 128, 0, st>>>(a); break;
     case 7: kubo_kernel<Draws, 7, kInstr, false><<<grid, 128, 0, st>>>(a); break;
+    case 8: kubo_kernel<Draws, 8, kInstr, false><<<grid, 128, 0, st>>>(a); break;
     default: kubo_kernel<Draws, 5, kInstr, false><<<grid, 128, 0, st>>>(a); break;
   }
 }
@@ -1505,6 +1505,7 @@ static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned 
         case 4: contact_kernel<PhiloxDraws, 4><<<grid, 128, smem, st>>>(a); break;
         case 6: contact_kernel<PhiloxDraws, 6><<<grid, 128, smem, st>>>(a); break;
         case 7: contact_kernel<PhiloxDraws, 7><<<grid, 128, smem, st>>>(a); break;
+        case 8: contact_kernel<PhiloxDraws, 8><<<grid, 128, smem, st>>>(a); break;
         default: contact_kernel<PhiloxDraws, 5><<<grid, 128, smem, st>>>(a); break;
       }
     }
@@ -1862,7 +1863,7 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
       require(value >= 0 && value <= 100, "hot_pct must be in [0, 100]");
       h->opt_hot_pct = value;
     } else if (k == "occupancy") {
-      require(value >= 4 && value <= 7, "occupancy must be 4 to 7 blocks per SM");
+      require(value >= 4 && value <= 8, "occupancy must be 4 to 8 blocks per SM");
       h->opt_occupancy = value;
     } else if (k == "dirs") {
       h->opt_dirs = value ? 1 : 0;

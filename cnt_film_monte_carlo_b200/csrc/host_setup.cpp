@@ -500,11 +500,11 @@ std::vector<SiteRec> make_site_records(const Sites& s, double velocity, std::vec
       r.q_left = segment_time(x, y, z, s.pos[0][(size_t)r.left], s.pos[1][(size_t)r.left], s.pos[2][(size_t)r.left], velocity);
     if (r.right > -1)
       r.q_right = segment_time(x, y, z, s.pos[0][(size_t)r.right], s.pos[1][(size_t)r.right], s.pos[2][(size_t)r.right], velocity);
-    r.total = r.inv_total = 0.0;
+    r.inv_total = 0.0;
     r.row_begin = r.row_len = 0;
     for (int k = 0; k < 8; ++k) r.guide[k] = 0;
-    r.spare = 0.0;
-    r.top = TopRec{0, 0, 0, 0, 0, 0, {-1, -1, -1}, 0};  // filled by the table build
+    for (int k = 0; k < 6; ++k) r.spare[k] = 0.0;
+    r.top = TopRec{0, 0, 0, -1, -1, -1, 0.0};  // filled by the table build
   }
   return rec;
 }

@@ -408,9 +408,10 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
 #endif
   // trap solver: this lane's site of the window
   int32_t  win_b = -1;
-  double   w_total = 0, w_inv = 0, w_lo0 = 0, w_hi0 = 0, w_lo1 = 0, w_hi1 = 0, w_lo2 = 0, w_hi2 = 0, w_qr = 0, w_ql = 0;
+  double   w_total = 0, w_inv = 0, w_qr = 0, w_ql = 0;
+  uint32_t w_iv0 = 0, w_iv1 = 0, w_iv2 = 0;  // top entries as intervals of the draw (hop_core.h SiteRec)
   int32_t  w_n0 = -1, w_n1 = -1, w_n2 = -1, w_left = -1, w_right = -1;
-  uint32_t w_rowlen = 0, w_flags = 0;
+  uint32_t w_flags = 0;
 
   auto start = [&]() {
     const uint32_t nc = L.ncross, np = L.nprobe, nr = L.nreinject, nf = L.nfast;
@@ -532,11 +533,10 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
             win_b = (int32_t)b;
             const SiteRec*  rec = a.T.site + (win_b + (lane - gbase));
             const SiteChain c = load_chain(rec);
-            const HopInfo   h = load_hop(rec);
             const TopLoaded t = load_top(&rec->top);
             w_left = c.left; w_right = c.right; w_qr = c.q_right; w_ql = c.q_left;
-            w_total = h.total; w_inv = h.inv_total; w_rowlen = h.row_len;
-            w_lo0 = t.lo0; w_hi0 = t.hi0; w_lo1 = t.lo1; w_hi1 = t.hi1; w_lo2 = t.lo2; w_hi2 = t.hi2;
+            w_total = t.total; w_inv = c.inv_total;
+            w_iv0 = t.iv0; w_iv1 = t.iv1; w_iv2 = t.iv2;
             w_n0 = t.nbr0; w_n1 = t.nbr1; w_n2 = t.nbr2;
             // what particle::fly does with the heading on this site (particle.cpp:20-34): bit 0 = heading after a start
             // to the right, bit 1 = after a start to the left, bit 2 = link-less or odd chain (generic path)
@@ -553,14 +553,11 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
           const int32_t my_site = win_b + (lane - gbase);
 #pragma unroll
           for (int k = 0; k < G; ++k) {
-            const int32_t r = (int32_t)__shfl_sync(gmask, D.r1, gbase + k);
-            const double  dice = div_by(w_total * (double)r, kRandMax, kInvRandMax);  // scatterer.cpp:17
-            const bool    in0 = (w_lo0 <= dice) && (dice < w_hi0);
-            const bool    in1 = (w_lo1 <= dice) && (dice < w_hi1);
-            const bool    in2 = (w_lo2 <= dice) && (dice < w_hi2);
+            const uint32_t u = __shfl_sync(gmask, D.r1, gbase + k) >> kTopBlockShift;  // scatterer.cpp:17 through the draw intervals
+            const bool    in0 = in_draw_blocks(w_iv0, u), in1 = in_draw_blocks(w_iv1, u), in2 = in_draw_blocks(w_iv2, u);
             const int32_t dest = in0 ? w_n0 : in1 ? w_n1 : w_n2;
             const int32_t di = dest - win_b;
-            const bool    ok = (in0 || in1 || in2) && w_rowlen != 0 && dest != my_site && di >= 0 && di < G;
+            const bool    ok = (in0 || in1 || in2) && w_n0 != kEmptyRow && dest != my_site && di >= 0 && di < G;
             tbl |= (ok ? (uint32_t)di : 15u) << (4 * k);
           }
           const unsigned zero2 = __ballot_sync(gmask, D.r2 == 0u) >> gbase;  // a zero free-flight draw is redrawn (scatterer.h:76-78)
@@ -660,7 +657,6 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
             if (!at) {
               L.px = px; L.py = py; L.pz = pz;
             }
-            L.total_valid = false;
           }
         }
       }
@@ -704,7 +700,7 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
           dt_rem -= t;  // particle.cpp:63
           const uint32_t room = (kInstr && trace) ? (uint32_t)(a.trace_cap - trace_base) : 0u;
           after_flight_scatter(L, a.T, D, leg, kInstr ? trace : nullptr, room, a.top_entries != 0);
-        } while (--left > 0 && (L.ff <= dt_rem) && !L.stuck && !(kDefer && L.total_valid && L.total >= a.deep_rate));
+        } while (--left > 0 && (L.ff <= dt_rem) && !L.stuck && !(kDefer && site_total(L, a.T) >= a.deep_rate));
         did_event = true;
       }
       CNTMC_SEG(L, 7);  // waiting for the other lanes of the warp to finish their events
@@ -713,7 +709,8 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
       if (kTrap && a.yield_on && did_step && !did_event && !finished && !L.stuck && !(site_total(L, a.T) >= a.deep_rate)) yield = true;
       finished = have && (finished || walk_finished || L.stuck);
       // lanes: landed in a deep trap, the trap solver takes over
-      const bool defer = !kTrap && deep_on && did_event && !finished && L.total_valid && L.total >= a.deep_rate;
+      bool defer = false;
+      if constexpr (!kTrap && deep_on) defer = did_event && !finished && site_total(L, a.T) >= a.deep_rate;
       const bool release = finished || defer || yield;
       if (__any_sync(kFullMask, release)) {
         int cls = 0;
@@ -829,7 +826,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const Tables T, const int
   const int      lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const bool     mine = e < P;
-  const int      cls = mine ? activity_class(load_hop(T.site + site[e]).total * dt, deep_thr) : 0;
+  const int      cls = mine ? activity_class(ro(&T.site[site[e]].top.total) * dt, deep_thr) : 0;
   file_excitons(q, mine, cls, (uint32_t)e, lane, lt_mask);
 }
 
@@ -1133,7 +1130,7 @@ __global__ void __launch_bounds__(256) site_records_kernel(const SiteSetupArgs a
     const double wx = a.px[r] - x, wy = a.py[r] - y, wz = a.pz[r] - z, nn = norm3(wx, wy, wz), den = (nn > 0) ? nn : 1.0;
     d.rx = wx / den; d.ry = wy / den; d.rz = wz / den;
   }
-  rec.top.nbr[0] = rec.top.nbr[1] = rec.top.nbr[2] = -1;  // rates, row and top entries: the table build
+  rec.top.nbr0 = rec.top.nbr1 = rec.top.nbr2 = -1;  // rates, row and top entries: the table build
   a.site[i] = rec;
   a.pos[i] = PosRec{x, y, z, 0.0};
   a.dir[i] = d;
@@ -1243,7 +1240,6 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
   if (!kFill) {
     a.deg[i] = d;
   } else {
-    a.site[i].total = acc;                  // scatterer.h:91  _max_rate = neighbors.back().first
     a.site[i].inv_total = d ? 1. / acc : 0.0;  // scatterer.h:92
     a.site[i].row_begin = (uint32_t)base;
     a.site[i].row_len = d;
@@ -1255,7 +1251,7 @@ __global__ void __launch_bounds__(128) csr_rows_kernel(const CsrArgs a) {
     build_guide(CumView{a.row + base}, d, acc, g8);  // reads back this thread's own row
 #pragma unroll
     for (int j = 0; j < kGuideBuckets; ++j) a.site[i].guide[j] = g8[j];
-    top.store(a.site[i].top);
+    top.store(a.site[i].top, acc, d);  // with scatterer.h:91  _max_rate = neighbors.back().first
     if (d == 0) atomicOr(a.flags + FLAG_EMPTY_ROW, 1);
     if (guard) {
       const unsigned long long k = atomicAdd(a.counters + CTR_GUARD, 1ULL);
@@ -1415,19 +1411,28 @@ __global__ void __launch_bounds__(128) csr_fill_warp_kernel(const CsrArgs a) {
   uint32_t g8[kGuideBuckets];
 #pragma unroll
   for (int j = 0; j < kGuideBuckets; ++j) g8[j] = __shfl_sync(kFullMask, gk, j);
+  // top entries as intervals of the draw (hop_core.h SiteRec): lane 2j bisects for the lower end of entry j, lane 2j+1 for its upper end
+  uint32_t rk = 0;
+  if (lane < 2 * kTopEntries) {
+    const int    j = lane >> 1;
+    const double x = (lane & 1) ? (j == 0 ? top[0].hi : j == 1 ? top[1].hi : top[2].hi) : (j == 0 ? top[0].lo : j == 1 ? top[1].lo : top[2].lo);
+    rk = first_draw_reaching(acc, x);
+  }
+  uint32_t r6[2 * kTopEntries];
+#pragma unroll
+  for (int j = 0; j < 2 * kTopEntries; ++j) r6[j] = __shfl_sync(kFullMask, rk, j);
   if (lane == 0) {
     SiteRec& r = a.site[i];
-    r.total = acc;                       // scatterer.h:91  _max_rate = neighbors.back().first
     r.inv_total = d ? 1. / acc : 0.0;   // scatterer.h:92
     r.row_begin = (uint32_t)base;
     r.row_len = d;
 #pragma unroll
     for (int j = 0; j < kGuideBuckets; ++j) r.guide[j] = (uint8_t)g8[j];
-    r.top.lo0 = top[0].lo; r.top.hi0 = top[0].hi;
-    r.top.lo1 = top[1].lo; r.top.hi1 = top[1].hi;
-    r.top.lo2 = top[2].lo; r.top.hi2 = top[2].hi;
-    r.top.nbr[0] = top[0].nbr; r.top.nbr[1] = top[1].nbr; r.top.nbr[2] = top[2].nbr;
-    r.top.pad = 0;
+    r.top.iv0 = draw_blocks(r6[0], r6[1]);
+    r.top.iv1 = draw_blocks(r6[2], r6[3]);
+    r.top.iv2 = draw_blocks(r6[4], r6[5]);
+    r.top.nbr0 = d ? top[0].nbr : kEmptyRow; r.top.nbr1 = top[1].nbr; r.top.nbr2 = top[2].nbr;
+    r.top.total = acc;                   // scatterer.h:91  _max_rate = neighbors.back().first
     if (d == 0) atomicOr(a.flags + FLAG_EMPTY_ROW, 1);
     if (guard) {
       const unsigned long long k = atomicAdd(a.counters + CTR_GUARD, 1ULL);

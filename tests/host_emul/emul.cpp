@@ -120,7 +120,6 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
             }
           }
       e->row_ptr[i + 1] = e->row_ptr[i] + d;
-      e->site[i].total = acc;
       e->site[i].inv_total = d ? 1. / acc : 0.0;
       {
         uint8_t g[kGuideBuckets];
@@ -129,7 +128,7 @@ int emul_kubo_init(Emul* e, int64_t n_tubes, int64_t n_cols, const double* pos_n
       }
       e->site[i].row_begin = (uint32_t)e->row_ptr[i];
       e->site[i].row_len = d;
-      top.store(e->site[i].top);
+      top.store(e->site[i].top, acc, d);
       e->guards += guard;
     }
     e->seg = make_segment_times(e->site);
@@ -168,8 +167,8 @@ void emul_sites(Emul* e, double* pos, double* orient, int32_t* left, int32_t* ri
   memcpy(left, e->sites.left.data(), N * 4);
   memcpy(right, e->sites.right.data(), N * 4);
   for (size_t i = 0; i < N; ++i) {
-    max_rate[i] = e->site[i].total;
-    inv[i] = 1. / e->site[i].total;
+    max_rate[i] = e->site[i].top.total;
+    inv[i] = 1. / e->site[i].top.total;
   }
 }
 void emul_csr(Emul* e, int64_t* row_ptr, int32_t* nbr, double* cum) {
@@ -310,17 +309,27 @@ int64_t emul_select_guided(const double* cum, int64_t d, int32_t r) {
   guide_bracket(g[0], g[1], (uint32_t)d, r, lo, hi);
   return select_via_entries(cum, d, lo, hi, dice);
 }
-// the decision of the top entries (after_flight_scatter): index of the top entry whose interval holds dice, or -1 (ordinary search needed)
-int64_t emul_select_top(const double* cum, int64_t d, double dice) {
+// the decision of the top entries (after_flight_scatter) for draw r: index of the top entry whose interval of the draw holds r,
+// or -1 (ordinary search needed); *dice receives the dice the ordinary search would use for r
+int64_t emul_select_top(const double* cum, int64_t d, int32_t r, double* dice) {
   TopEntries top;
   top.clear();
   for (int64_t k = 0; k < d; ++k) top.add(k ? cum[k] - cum[k - 1] : cum[0], k ? cum[k - 1] : -1.0, cum[k], (int32_t)k);
-  TopRec r{};
-  top.store(r);
-  if (r.lo0 <= dice && dice < r.hi0) return r.nbr[0];
-  if (r.lo1 <= dice && dice < r.hi1) return r.nbr[1];
-  if (r.lo2 <= dice && dice < r.hi2) return r.nbr[2];
+  TopRec t{};
+  top.store(t, cum[d - 1], (uint32_t)d);
+  *dice = dice_of(cum[d - 1], (uint32_t)r);
+  const uint32_t u = (uint32_t)r >> kTopBlockShift;
+  if (in_draw_blocks(t.iv0, u)) return t.nbr0;
+  if (in_draw_blocks(t.iv1, u)) return t.nbr1;
+  if (in_draw_blocks(t.iv2, u)) return t.nbr2;
   return -1;
+}
+// first_draw_reaching against its definition: the smallest draw whose dice is >= x (checked on both sides of the answer)
+int64_t emul_first_draw_reaching(double total, double x) {
+  const uint32_t r = first_draw_reaching(total, x);
+  if (r <= 0x7fffffffu && !(dice_of(total, r) >= x)) return -1;
+  if (r > 0u && dice_of(total, r - 1u) >= x) return -2;
+  return (int64_t)r;
 }
 int64_t emul_select_full(const double* cum, int64_t d, double dice) { return select_via_entries(cum, d, 0u, (uint32_t)d - 1u, dice); }
 // div_by against the division it replaces: number of operands (out of n) whose quotients differ

@@ -93,24 +93,53 @@ def test_select_entry_equals_reference_loop():
 
 
 def test_top_entries_decide_exactly_what_the_reference_loop_decides():
-    """The shortcut of the event path: a dice inside the interval of one of the three widest entries selects that entry."""
+    """The shortcut of the event path: a draw inside the stored draw interval of one of the three widest entries selects that
+    entry -- exactly the entry the reference's comparison of doubles selects for the dice of that draw.  (Intervals are stored in
+    whole blocks of 2^16 draws, rounded inwards, so draws next to an interval's end are left to the ordinary search.)"""
     import ctypes
     e = Emul(base_mc())
     e.L.emul_select_top.restype = ctypes.c_int64
-    e.L.emul_select_top.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double]
+    e.L.emul_select_top.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
     rng = np.random.default_rng(23)
-    decided = 0
+    decided = undecided = 0
+    RAND_MAX = 2147483647
     for _ in range(3000):
         d = int(rng.integers(1, 60))
         rates = rng.random(d) * (rng.random(d) > 0.25)
         rates[rng.integers(0, d, size=int(rng.integers(0, 4)))] *= 1e3   # a few dominant entries, as on hot sites
         c = np.cumsum(rates)
-        for dice in (0.0, c[-1], c[-1] * rng.random(), float(rng.choice(c)), np.nextafter(float(rng.choice(c)), 0), np.nextafter(float(rng.choice(c)), np.inf)):
-            k = e.L.emul_select_top(c.ctypes.data, d, ctypes.c_double(dice))
+        if c[-1] == 0.0:
+            continue
+        # draws at and around the images of the interval ends (block boundaries included), the ends of the range, random ones
+        rs = {0, 1, 65535, 65536, RAND_MAX - 65536, RAND_MAX - 1, RAND_MAX} | {int(x) for x in rng.integers(0, RAND_MAX + 1, size=4)}
+        for x in rng.choice(c, size=3):
+            r0 = int(min(RAND_MAX, max(0, round(float(x) / c[-1] * RAND_MAX))))
+            for r in (r0 - 65536, r0 - 1, r0, r0 + 1, r0 + 65536, (r0 >> 16) << 16, ((r0 >> 16) << 16) - 1, ((r0 >> 16) + 1) << 16):
+                if 0 <= r <= RAND_MAX:
+                    rs.add(r)
+        for r in rs:
+            dice = ctypes.c_double()
+            k = e.L.emul_select_top(c.ctypes.data, d, r, ctypes.byref(dice))
             if k >= 0:
-                assert k == T1m.select(c, dice)
+                assert k == T1m.select(c, dice.value)
                 decided += 1
-    assert decided > 4000
+            else:
+                undecided += 1
+    assert decided > 10000 and undecided > 1000
+
+
+def test_first_draw_reaching_is_the_smallest_draw_whose_dice_reaches_the_bound():
+    import ctypes
+    e = Emul(base_mc())
+    f = e.L.emul_first_draw_reaching
+    f.restype = ctypes.c_int64
+    f.argtypes = [ctypes.c_double, ctypes.c_double]
+    rng = np.random.default_rng(5)
+    assert f(1.0, -1.0) == 0 and f(1.0, 0.0) == 0 and f(3.7e12, 3.8e12) == 1 << 31
+    for _ in range(20000):
+        total = float(10.0 ** rng.uniform(-3, 15) * rng.uniform(1, 10))
+        x = total * float(rng.random()) if rng.random() < 0.9 else float(np.nextafter(total, rng.choice([0.0, np.inf])))
+        assert f(total, x) >= 0
 
 
 def test_top_entries_path_is_bit_identical_and_matches_oracle(golden):
