@@ -41,7 +41,7 @@ TRIM_INPUT_JSON = {"xlim": [-1e-6, 1e-6], "ylim": [0, 1e-7], "zlim": [-1e-6, 1e-
 WORKLOADS = {
     "C1": dict(film="C1", mode="kubo", dt=1e-15, trim=TRIM_INPUT_JSON, excitons=2000, intervals=20000, chunk=4096, steps=10, scaling="weak",
                text="C1: input.json verbatim (trim limits, dt 1e-15 s, 2000 excitons) on the 200-tube x 100-site stand-in film (seed 1234)"),
-    "C2": dict(film="C2", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=1_000_000, intervals=100, chunk=64, steps=145, scaling="weak",
+    "C2": dict(film="C2", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=1_000_000, intervals=100, chunk=100, steps=145, scaling="weak",
                text="C2: 1000-tube x 100-site random CNT film (seed 1234), forster table 21x11x11x11, cutoff 20 nm"),
     "C3": dict(film="C2", mode="kubo", dt=DT, trim=TRIM_WIDE, excitons=None, intervals=100, chunk=64, steps=5, scaling="strong",
                text="C3: C2 film, a fixed population (--excitons-total) split over the ranks by global id"),
@@ -488,7 +488,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": wl["text"], "excitons_per_gpu": P, "excitons_total": P_all, "sites": eng.num_sites(), "dt_s": dt,
                        "intervals_per_step": n_int, "hops_per_step": hops_total / args.steps,
                        "l2": "flushed between timed steps (256 MiB fill, outside the events)",
-                       "chunk_steps": args.chunk or wl["chunk"], "hot_pct": args.hot_pct, "occupancy": args.occupancy,
+                       "chunk_steps": args.chunk or wl["chunk"], "hot_pct": args.hot_pct, "occupancy": int(eng.get_option("occupancy")),
                        "options": args.opt, "setup_s": round(t_setup, 2), "table_build_s": eng.csr_build_seconds(),
                        "parallelism": "exciton sharding x%d, tables replicated, 1 all-reduce/step" % world,
                        "msd_last_m2": acc["msd"]},
@@ -733,7 +733,7 @@ def main():
     ap.add_argument("--hot-pct", type=int, default=30, help="share of blocks serving the most active excitons first")
     ap.add_argument("--opt", action="append", default=[], help="extra engine option name=value (repeatable)")
     ap.add_argument("--top-entries", type=int, default=1, help="1: the three widest entries of a row are tried before the row is searched")
-    ap.add_argument("--occupancy", type=int, default=7, help="resident 128-thread blocks per SM of the hop kernel (4 to 7)")
+    ap.add_argument("--occupancy", type=int, default=0, help="resident 128-thread blocks per SM of the hop kernel (4 to 8; 0 = the engine's choice: 7, or 8 when the tables exceed L2)")
     ap.add_argument("--stage-mb", type=int, default=0, help="cap on the (step, exciton) staging buffer in MiB (0 = engine default)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-excitons", type=int, default=8000)

@@ -210,7 +210,8 @@ struct cntmc_handle {
                                  // the deferred excitons while they arrive (see hop_loop)
   int64_t opt_overlap_trap_blocks = 1;  // blocks per SM of the trap kernel in overlap mode; the lane kernel takes the rest of five
   int64_t opt_deep_rounds = 2;  // 2: the trap solver hands excitons that left their trap back to the lanes once per launch
-  int64_t opt_occupancy = 7;   // resident 128-thread blocks per SM the hop kernel is compiled for (4 to 7; 7 = 72 registers)
+  int64_t opt_occupancy = 0;   // resident 128-thread blocks per SM the hop kernel is compiled for (4 to 8); 0 = by table size, see occupancy_of
+  int64_t l2_bytes = -1;
   int64_t opt_stage_mb = 0;  // cap on the (step, exciton) staging buffer in MiB; shortens the launches if needed.
                              // 0 = a third of the device memory that is free when the buffer is first sized
   int     sm_count = 0;
@@ -308,6 +309,21 @@ void need_rates(const cntmc_t* h) {
 
 void use_device(const cntmc_t* h) {
   if (h->device >= 0) CUDA_CHECK(cudaSetDevice(h->device));
+}
+// Resident blocks per SM of the hop kernels.  More warps hide more of the dependent-gather latency and cost registers: 7 blocks
+// (72 registers, no spills) is the best measured setting while the tables live in L2; once the rows come from HBM the longer
+// latency pays for an eighth block (64 registers, 16 bytes of spills): C4 1.02e10 -> 1.07e10 hops/s, C2 7.3e9 -> 6.9e9.
+int64_t occupancy_of(cntmc_t* h) {
+  if (h->opt_occupancy != 0) return h->opt_occupancy;
+  if (h->l2_bytes < 0) {
+    int dev = 0, l2 = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+    h->l2_bytes = l2;
+  }
+  const int64_t tables = (int64_t)h->nnz * (int64_t)sizeof(RowEntry) +
+                         (int64_t)h->sites.N * (int64_t)(sizeof(SiteRec) + sizeof(PosRec) + sizeof(DirRec) + sizeof(double));
+  return tables > h->l2_bytes ? 8 : 7;
 }
 
 void require(bool ok, const char* msg) {
@@ -712,7 +728,7 @@ void launch_kubo_i(cntmc_t* h, const KuboArgs& a, unsigned grid, cudaStream_t st
       return;
     }
   }
-  switch (h->opt_occupancy) {
+  switch (occupancy_of(h)) {
     case 4: kubo_kernel<Draws, 4, kInstr, false><<<grid, 128, 0, st>>>(a); break;
     case 6: kubo_kernel<Draws, 6, kInstr, false><<<grid, 128, 0, st>>>(a); break;
     case 7: kubo_kernel<Draws, 7, kInstr, false><<<grid, 128, 0, st>>>(a); break;
@@ -775,7 +791,7 @@ void kubo_step_device(cntmc_t* h, double dt, int64_t nsteps, double* dev_sums) {
   // (CNTMC_DBG_BLOCKS_PER_SM: fewer resident blocks than the kernel was compiled for -- separates the price of a variant's spills
   // from the gain of its extra blocks, profiles/round2_trap_solver.txt section 15)
   const char*    dbg_bps = getenv("CNTMC_DBG_BLOCKS_PER_SM");
-  const int64_t  bps = dbg_bps ? atoll(dbg_bps) : h->opt_occupancy;
+  const int64_t  bps = dbg_bps ? atoll(dbg_bps) : occupancy_of(h);
   const unsigned grid = (unsigned)std::min<int64_t>(want, std::max<int64_t>(1, (int64_t)h->sm_count * bps / h->grid_share));
   h->last_chunk = chunk;
   h->d_stage.alloc((size_t)chunk * (size_t)h->P);
@@ -1256,7 +1272,7 @@ int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P,
         cntmc_handle* s = h->slices[(size_t)k].get();
         const size_t  off = n * (size_t)k / (size_t)K, cnt = n * (size_t)(k + 1) / (size_t)K - off;
         s->T = h->T;
-        s->opt_chunk = h->opt_chunk; s->opt_hot_pct = h->opt_hot_pct; s->opt_occupancy = h->opt_occupancy;
+        s->opt_chunk = h->opt_chunk; s->opt_hot_pct = h->opt_hot_pct; s->opt_occupancy = occupancy_of(h);
         s->opt_top_entries = h->opt_top_entries; s->opt_deep_thr = h->opt_deep_thr; s->opt_deep_blocks = h->opt_deep_blocks;
         s->opt_deep_rounds = h->opt_deep_rounds; s->opt_trap_burst = h->opt_trap_burst;
         s->opt_deep_overlap = h->opt_deep_overlap; s->opt_overlap_trap_blocks = h->opt_overlap_trap_blocks;
@@ -1470,7 +1486,7 @@ static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned 
     }
     require(W < (1ll << 32), "more than 2^32 excitons in one contact launch: lower chunk_steps");  // work items are 32-bit indices
     h->reserve_contact(W, h->P);
-    const unsigned grid = (unsigned)std::min<int64_t>((W + 127) / 128, (int64_t)h->sm_count * h->opt_occupancy);
+    const unsigned grid = (unsigned)std::min<int64_t>((W + 127) / 128, (int64_t)h->sm_count * occupancy_of(h));
     set_u64_kernel<<<1, 1, 0, st>>>(h->d_counters.p + CTR_QUEUE, (unsigned long long)grid * 128ull);
     ContactArgs a{};
     a.T = h->T;
@@ -1501,7 +1517,7 @@ static void contact_step_device(cntmc_t* h, double dt, int64_t nsteps, unsigned 
         throw ReplayError("the replayed draw lists do not cover the excitons this call creates");
       contact_kernel<ReplayDraws, 5><<<grid, 128, smem, st>>>(a);
     } else {
-      switch (h->opt_occupancy) {
+      switch (occupancy_of(h)) {
         case 4: contact_kernel<PhiloxDraws, 4><<<grid, 128, smem, st>>>(a); break;
         case 6: contact_kernel<PhiloxDraws, 6><<<grid, 128, smem, st>>>(a); break;
         case 7: contact_kernel<PhiloxDraws, 7><<<grid, 128, smem, st>>>(a); break;
@@ -1863,7 +1879,7 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
       require(value >= 0 && value <= 100, "hot_pct must be in [0, 100]");
       h->opt_hot_pct = value;
     } else if (k == "occupancy") {
-      require(value >= 4 && value <= 8, "occupancy must be 4 to 8 blocks per SM");
+      require(value == 0 || (value >= 4 && value <= 8), "occupancy must be 4 to 8 blocks per SM, or 0 (by table size)");
       h->opt_occupancy = value;
     } else if (k == "dirs") {
       h->opt_dirs = value ? 1 : 0;
@@ -1888,7 +1904,7 @@ int cntmc_set_option(cntmc_t* h, const char* name, int64_t value) {
 int64_t cntmc_get_option(const cntmc_t* h, const char* name) {
   const std::string k = name ? name : "";
   if (k == "chunk_steps") return h->opt_chunk;
-  if (k == "occupancy") return h->opt_occupancy;
+  if (k == "occupancy") return h->initialised ? occupancy_of(const_cast<cntmc_t*>(h)) : h->opt_occupancy;  // 0 = by table size, resolved by init
   if (k == "hot_pct") return h->opt_hot_pct;
   if (k == "deep_thr") return h->opt_deep_thr;
   if (k == "deep_blocks") return h->opt_deep_blocks;

@@ -107,7 +107,7 @@ def test_chunking_scheduling_and_occupancy_do_not_change_results():
     states, msds = [], []
     # the first run is the plain loop (no trap solver); every other scheduling must give the same bits
     for opts in (dict(chunk_steps=64, occupancy=6, deep_thr=0), dict(chunk_steps=7, occupancy=4, deep_thr=16), dict(chunk_steps=1, deep_thr=8, deep_rounds=1),
-                 dict(chunk_steps=200, occupancy=5, deep_thr=0), dict(chunk_steps=50, occupancy=7, deep_thr=0), dict(chunk_steps=64, stage_mb=1, deep_thr=16, deep_blocks=1),
+                 dict(chunk_steps=200, occupancy=5, deep_thr=0), dict(chunk_steps=31, occupancy=7, deep_thr=0), dict(chunk_steps=50, occupancy=8, deep_thr=0), dict(chunk_steps=64, occupancy=0, hot_pct=10, deep_thr=0), dict(chunk_steps=64, stage_mb=1, deep_thr=16, deep_blocks=1),
                  dict(chunk_steps=8, hot_pct=0, deep_thr=16), dict(chunk_steps=3, hot_pct=100, deep_thr=16, deep_blocks=1),
                  dict(chunk_steps=8, hot_pct=30, occupancy=6, deep_thr=1, deep_blocks=2),
                  dict(top_entries=0), dict(top_entries=1, chunk_steps=16, deep_thr=0), dict(top_entries=0, runs=0, hot_pct=50),
