@@ -730,7 +730,7 @@ def main():
     ap.add_argument("--c1-pop", type=int, default=22_000_000, help="C5: contact-1 population per GPU (~5.7x as many excitons alive)")
     ap.add_argument("--intervals", type=int, default=0, help="sampling intervals per bench step (0 = the workload's own)")
     ap.add_argument("--chunk", type=int, default=0, help="time steps per kernel launch (0 = the workload's own)")
-    ap.add_argument("--hot-pct", type=int, default=30, help="share of blocks serving the most active excitons first")
+    ap.add_argument("--hot-pct", type=int, default=25, help="share of blocks serving the most active excitons first")
     ap.add_argument("--opt", action="append", default=[], help="extra engine option name=value (repeatable)")
     ap.add_argument("--top-entries", type=int, default=1, help="1: the three widest entries of a row are tried before the row is searched")
     ap.add_argument("--occupancy", type=int, default=0, help="resident 128-thread blocks per SM of the hop kernel (4 to 8; 0 = the engine's choice: 7, or 8 when the tables exceed L2)")

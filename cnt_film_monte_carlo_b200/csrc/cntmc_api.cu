@@ -199,7 +199,7 @@ struct cntmc_handle {
   int64_t opt_dirs = 1;         // last legs that leave from a site use stored unit vectors
   int64_t opt_runs = 1;         // chain walks over memory-consecutive sites read segment times instead of chasing records
   int64_t opt_top_entries = 1;  // the three widest entries of a row are tried before the row is searched
-  int64_t opt_hot_pct = 30;   // share of the lane blocks that serve the most active classes first
+  int64_t opt_hot_pct = 25;   // share of the lane blocks that serve the most active classes first
   int64_t opt_gid_base = 0;   // contact mode: stream ids start at opt_gid_base * 2^56 (cntmc_multi gives every GPU its own range)
   int64_t opt_deep_thr = 0;   // Gamma*dt from which an exciton belongs to the trap solver (0: no trap solver, the default:
                               // parity-green but slower on every workload measured, profiles/round2_trap_solver.txt)

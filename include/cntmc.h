@@ -175,7 +175,7 @@ int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites);
 
 /* ---- tuning (never changes results) ------------------------------------------------------------------------------------
  * chunk_steps  time steps per hop-kernel launch (default 64)          stage_mb     cap on the staging buffer in MiB (0 = auto)
- * hot_pct      share of the lane blocks that serve the most active excitons first (default 30)
+ * hot_pct      share of the lane blocks that serve the most active excitons first (default 25; re-tuned for 7 blocks per SM: 22-26 within 1 %, 20 and 35 lose 3-8 %)
  * deep_thr     Gamma*dt from which an exciton is handed to the trap solver, a second kernel that walks trapped excitons
  *              from a register-resident window of site records (default 0 = off: bit-identical results, but slower on
  *              every workload measured so far); deep_blocks (blocks per SM of its launch, default 4), deep_rounds
