@@ -316,7 +316,7 @@ struct GroupDraws {
     nd0 = ndraw;
     uint32_t    n = ndraw + 2u * (uint32_t)j;
     PhiloxDraws t = base;
-    t.blk = 0xffffffffu;
+    t.have = false;
     r1 = (uint32_t)t.next(n);
     r2 = (uint32_t)t.next(n);
     lg = r2 ? fast_log_unit(div_by((double)r2, kRandMax, kInvRandMax)) : 0.0;
@@ -669,6 +669,10 @@ __device__ __forceinline__ void hop_loop(const KuboArgs& a, double (&s_delta)[3]
         const Leg    leg = fly(L, a.T, t, true);
         L.dx = s_delta[0][tid]; L.dy = s_delta[1][tid]; L.dz = s_delta[2][tid];
         after_flight_step_end(L, a.T, D, leg, t, s_old[0][tid], s_old[1][tid], s_old[2][tid]);
+        if (!kInstr && L.nreinject) {  // counted at once (re-injections are rare): one register less across the loop
+          if (leader) atomicAdd(a.counters + CTR_REINJECT, 1ULL);
+          L.nreinject = 0;
+        }
         if (leader) {
           // streaming stores: written once, read once by the reduction, must not evict the tables from L2
           double2* rec = reinterpret_cast<double2*>(a.stage + ((size_t)step * (size_t)a.P + (size_t)e));
