@@ -324,6 +324,9 @@ int64_t emul_select_top(const double* cum, int64_t d, int32_t r, double* dice) {
   if (in_draw_blocks(t.iv2, u)) return t.nbr2;
   return -1;
 }
+// the packed block interval of the draws [rlo, rhi) (hop_core.h draw_blocks) and the membership test the event applies to it
+uint32_t emul_draw_blocks(uint32_t rlo, uint32_t rhi) { return draw_blocks(rlo, rhi); }
+int emul_in_draw_blocks(uint32_t iv, uint32_t r) { return in_draw_blocks(iv, r >> kTopBlockShift) ? 1 : 0; }
 // first_draw_reaching against its definition: the smallest draw whose dice is >= x (checked on both sides of the answer)
 int64_t emul_first_draw_reaching(double total, double x) {
   const uint32_t r = first_draw_reaching(total, x);

@@ -128,6 +128,40 @@ def test_top_entries_decide_exactly_what_the_reference_loop_decides():
     assert decided > 10000 and undecided > 1000
 
 
+def test_draw_block_intervals_are_rounded_inwards_and_as_wide_as_possible():
+    """TopRec stores [rlo, rhi) as whole blocks of 2^16 draws: every draw the packed interval accepts lies in [rlo, rhi), and the
+    blocks just outside it do not fit (so only draws in the two boundary blocks are left to the ordinary search)."""
+    import ctypes
+    e = Emul(base_mc())
+    pack, member = e.L.emul_draw_blocks, e.L.emul_in_draw_blocks
+    pack.restype = ctypes.c_uint32
+    pack.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
+    member.restype = ctypes.c_int
+    member.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
+    rng = np.random.default_rng(99)
+    B = 1 << 16
+    cases = [(0, 0), (0, 1 << 31), (0, B), (1, B), (0, B - 1), (B, 2 * B), (B - 1, 2 * B + 1), ((1 << 31) - B, 1 << 31), ((1 << 31) - 1, 1 << 31), (1 << 31, 1 << 31)]
+    for _ in range(20000):
+        lo = int(rng.integers(0, (1 << 31) + 1))
+        hi = int(min(1 << 31, lo + int(rng.integers(0, 1 << int(rng.integers(1, 32))))))
+        cases.append((lo, hi))
+    for lo, hi in cases:
+        iv = pack(lo, hi)
+        blo, n = iv & 0xffff, iv >> 16
+        assert blo * B >= lo and (n == 0 or (blo + n) * B <= hi)                  # inside [rlo, rhi)
+        if n:
+            assert (blo - 1) * B < lo or blo == 0 and lo == 0 or (blo - 1) * B < lo  # the block before does not fit
+            assert (blo + n + 1) * B > hi                                            # nor the block after
+        else:
+            assert hi - lo < 2 * B - 1 or hi <= lo                                   # no whole block fits
+        for r in {lo, max(lo, hi - 1), (lo + hi) // 2, blo * B, max(0, blo * B - 1), min((1 << 31) - 1, (blo + n) * B), (blo + n) * B - 1}:
+            if 0 <= r < (1 << 31):
+                if member(iv, r):
+                    assert lo <= r < hi
+                elif n:
+                    assert not (blo * B <= r < (blo + n) * B)
+
+
 def test_first_draw_reaching_is_the_smallest_draw_whose_dice_reaches_the_bound():
     import ctypes
     e = Emul(base_mc())
