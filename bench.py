@@ -733,7 +733,7 @@ def main():
     ap.add_argument("--hot-pct", type=int, default=25, help="share of blocks serving the most active excitons first")
     ap.add_argument("--opt", action="append", default=[], help="extra engine option name=value (repeatable)")
     ap.add_argument("--top-entries", type=int, default=1, help="1: the three widest entries of a row are tried before the row is searched")
-    ap.add_argument("--occupancy", type=int, default=0, help="resident 128-thread blocks per SM of the hop kernel (4 to 8; 0 = the engine's choice: 7, or 8 when the tables exceed L2)")
+    ap.add_argument("--occupancy", type=int, default=0, help="resident 128-thread blocks per SM of the hop kernel (4 to 8; 0 = the engine's choice: 8 when the tables exceed L2 or for 2e6 excitons and more, else 7)")
     ap.add_argument("--stage-mb", type=int, default=0, help="cap on the (step, exciton) staging buffer in MiB (0 = engine default)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-excitons", type=int, default=8000)

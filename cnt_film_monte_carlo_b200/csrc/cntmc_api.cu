@@ -311,8 +311,10 @@ void use_device(const cntmc_t* h) {
   if (h->device >= 0) CUDA_CHECK(cudaSetDevice(h->device));
 }
 // Resident blocks per SM of the hop kernels.  More warps hide more of the dependent-gather latency and cost registers: 7 blocks
-// (72 registers, no spills) is the best measured setting while the tables live in L2; once the rows come from HBM the longer
-// latency pays for an eighth block (64 registers, 16 bytes of spills): C4 1.02e10 -> 1.07e10 hops/s, C2 7.3e9 -> 6.9e9.
+// (70 registers, no spills) against 8 (64 registers, 16 bytes of spills in a cold branch) measured on one B200, hops/s:
+//   tables in HBM (C4)                    1.03e10 / 1.10e10      Green-Kubo, tables in L2: 1e6 excitons 7.57e9 / 7.55e9,
+//   contacts, tables in L2 (C5)           1.53e10 / 1.49e10        2e6 8.74e9 / 8.87e9, 6e6 9.61e9 / 9.89e9, 1e8 6.93e9 / 7.16e9
+// so: 8 once the rows come from HBM, or for a Green-Kubo population of two million and more; 7 otherwise.
 int64_t occupancy_of(cntmc_t* h) {
   if (h->opt_occupancy != 0) return h->opt_occupancy;
   if (h->l2_bytes < 0) {
@@ -323,7 +325,8 @@ int64_t occupancy_of(cntmc_t* h) {
   }
   const int64_t tables = (int64_t)h->nnz * (int64_t)sizeof(RowEntry) +
                          (int64_t)h->sites.N * (int64_t)(sizeof(SiteRec) + sizeof(PosRec) + sizeof(DirRec) + sizeof(double));
-  return tables > h->l2_bytes ? 8 : 7;
+  if (tables > h->l2_bytes) return 8;
+  return (!h->contact_mode && h->P >= 2000000) ? 8 : 7;
 }
 
 void require(bool ok, const char* msg) {

@@ -189,7 +189,7 @@ int cntmc_trace_get(const cntmc_t* h, int32_t* counts, int32_t* sites);
  * host_slices  cntmc_kubo_step_host_state steps the uploaded population in this many slices on their own streams so that
  *              the copies of one overlap the kernels of the others (default 4; populations below 65536 per slice: 1)
  * gid_base_shift56  contact mode: stream ids start at value * 2^56 (cntmc_multi keeps the GPUs' streams apart with it)
- * occupancy    resident 128-thread blocks per SM the hop kernel is compiled for (4 to 8; default 0 = 7, or 8 when the tables exceed the L2 cache)
+ * occupancy    resident 128-thread blocks per SM the hop kernel is compiled for (4 to 8; default 0 = 8 when the tables exceed the L2 cache or a Green-Kubo population has 2e6 excitons or more, else 7)
  * top_entries  1: the three widest entries of a row are tried before the row is searched (default)
  * runs         1: chain walks over memory-consecutive sites read segment times instead of chasing records (default)
  * dirs         1: last legs that leave from a site use stored unit vectors (default)
