@@ -1270,6 +1270,7 @@ int cntmc_kubo_step_host_state(cntmc_t* h, double dt, int64_t nsteps, int64_t P,
         CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
       }
       while ((int)h->slices.size() < K) make_slice(h);
+      h->P = P;  // (the blocks per SM follow the whole population, occupancy_of)
       std::vector<std::vector<double>> rows((size_t)K, std::vector<double>((size_t)nsteps * 4));
       for (int k = 0; k < K; ++k) {
         cntmc_handle* s = h->slices[(size_t)k].get();
