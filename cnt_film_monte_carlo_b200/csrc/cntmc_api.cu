@@ -350,7 +350,7 @@ void check_flags(cntmc_t* h) {
     static_assert(FLAG_STUCK == 0 && FLAG_REPLAY == 1, "the two run-time flags are the first two words");
   }
   if (flags[FLAG_REPLAY]) throw ReplayError("a replayed draw list ran out before the end of the run");
-  if (flags[FLAG_STUCK]) throw StateError("an exciton exceeded the chain-walk guard (coincident chain sites?)");
+  if (flags[FLAG_STUCK]) throw StateError("an exciton exceeded the chain-walk guard (coincident chain sites?) or met a chain-walk operand outside [2^-400, 2^401) m");
 }
 
 // monte_carlo::create_scattering_table, "davoody" branch (monte_carlo.cpp:32-49): tube physics for the input's tubes, then
